@@ -1,0 +1,555 @@
+// C ABI of the mehhua scoring path (see include/mehhua.h).  Host side: argument validation, the
+// batch Plan, workspace carving and kernel launches.  No torch types, no hidden allocation except
+// inside the explicit host-buffer context.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "k1_alpha_topk.cuh"
+#include "k2_dirichlet.cuh"
+#include "k3_hua.cuh"
+#include "k4_pool_topk.cuh"
+
+using namespace mehhua;
+
+namespace {
+
+thread_local char g_err[256] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return MEHHUA_E_CUDA;
+}
+int arg_fail(const char* what) {
+  snprintf(g_err, sizeof(g_err), "invalid argument: %s", what);
+  return MEHHUA_E_ARG;
+}
+#define CU(call)                                            \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);     \
+  } while (0)
+#define LAUNCHED(name)                                      \
+  do {                                                      \
+    g_launches.fetch_add(1, std::memory_order_relaxed);     \
+    cudaError_t e_ = cudaGetLastError();                    \
+    if (e_ != cudaSuccess) return cuda_fail(e_, name);      \
+  } while (0)
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool need_ptrs, Plan* out) {
+  if (!cfg || !lv) return arg_fail("null config / levels");
+  if (cfg->num_levels < 1 || cfg->num_levels > kMaxLevels) return arg_fail("num_levels must be 1..8");
+  if (cfg->head != MEHHUA_HEAD_RETINA && cfg->head != MEHHUA_HEAD_SSD) return arg_fail("head");
+  if (cfg->c_out < 2 || cfg->c_out > 1024) return arg_fail("c_out must be 2..1024");
+  if (cfg->max_per_img < 1 || cfg->max_per_img > MEHHUA_MAX_DETS) return arg_fail("max_per_img must be 1..256");
+  if (cfg->nms_pre > MEHHUA_MAX_NMS_PRE) return arg_fail("nms_pre must be <= 4096");
+  if (B < 1 || B > 1024) return arg_fail("batch must be 1..1024");
+  if (cfg->pair_cap < 1) return arg_fail("pair_cap must be positive");
+  if (cfg->n_samples < 1) return arg_fail("n_samples must be positive");
+  for (int a : {cfg->agg_object, cfg->agg_scale, cfg->agg_class})
+    if (a < MEHHUA_AGG_SUM || a > MEHHUA_AGG_MAX) return arg_fail("aggregation op");
+  Plan p;
+  memset(&p, 0, sizeof(p));
+  p.S = cfg->num_levels; p.B = B; p.C = cfg->c_out; p.head = cfg->head;
+  p.num_fg = cfg->head == MEHHUA_HEAD_SSD ? cfg->c_out - 1 : cfg->c_out;
+  long long n_off = 0, k_off = 0, tile0 = 0;
+  for (int s = 0; s < p.S; ++s) {
+    LevelDev& L = p.lv[s];
+    if (lv[s].H < 1 || lv[s].W < 1 || lv[s].A < 1) return arg_fail("level geometry");
+    if (need_ptrs && (!lv[s].logits || !lv[s].deltas || !lv[s].lambda || !lv[s].anchors))
+      return arg_fail("null level pointer");
+    L.logits = lv[s].logits; L.deltas = lv[s].deltas; L.lam = lv[s].lambda; L.anchors = lv[s].anchors;
+    L.H = lv[s].H; L.W = lv[s].W; L.A = lv[s].A; L.HW = L.H * L.W;
+    const long long n = (long long)L.HW * L.A;
+    if (n > (1ll << 30)) return arg_fail("level too large");
+    L.n = (int)n;
+    L.topk = (cfg->nms_pre > 0 && cfg->nms_pre < L.n) ? 1 : 0;
+    L.k = L.topk ? cfg->nms_pre : L.n;
+    L.n_off = (int)n_off; L.k_off = (int)k_off;
+    L.tpp = (L.HW + kK1aThreads - 1) / kK1aThreads;
+    L.tile0 = (int)tile0;
+    n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
+  }
+  if (n_off > (1ll << 30) || k_off > (1 << 20) || tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
+  p.N = (int)n_off; p.K = (int)k_off; p.tiles_per_image = (int)tile0;
+  p.nms_pre = cfg->nms_pre; p.max_per_img = cfg->max_per_img; p.pair_cap = cfg->pair_cap;
+  p.n_samples = cfg->n_samples; p.use_lambda = cfg->use_lambda;
+  p.agg_object = cfg->agg_object; p.agg_scale = cfg->agg_scale; p.agg_class = cfg->agg_class;
+  p.cls_w = cfg->cls_w; p.rescale = cfg->rescale;
+  p.score_thr = cfg->score_thr; p.nms_iou = cfg->nms_iou; p.fg_thr = cfg->fg_thr;
+  p.obj_thr = cfg->obj_thr; p.cluster_iou = cfg->cluster_iou;
+  p.lambda_scale = cfg->lambda_scale; p.lambda_eps = cfg->lambda_eps;
+  for (int i = 0; i < 4; ++i) { p.means[i] = cfg->means[i]; p.stds[i] = cfg->stds[i]; }
+  if (!(cfg->wh_ratio_clip > 0.f)) return arg_fail("wh_ratio_clip");
+  p.max_ratio = (float)std::fabs(std::log((double)cfg->wh_ratio_clip));
+  p.seed = cfg->seed;
+  *out = p;
+  return 0;
+}
+
+size_t carve(const Plan& p, void* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t o_keys = take((size_t)p.B * p.N * sizeof(float));
+  const size_t o_cand = take((size_t)p.B * p.K * p.num_fg * sizeof(unsigned long long));
+  const size_t o_cnt = take((size_t)p.B * sizeof(int));
+  const size_t o_maxc = take((size_t)p.B * sizeof(unsigned));
+  const size_t o_status = take(sizeof(unsigned));
+  const size_t o_work = take(4 * sizeof(int));
+  if (ws) {
+    char* b = static_cast<char*>(base);
+    ws->keys = reinterpret_cast<float*>(b + o_keys);
+    ws->cand = reinterpret_cast<unsigned long long*>(b + o_cand);
+    ws->cand_cnt = reinterpret_cast<int*>(b + o_cnt);
+    ws->cand_maxc = reinterpret_cast<unsigned*>(b + o_maxc);
+    ws->status = reinterpret_cast<unsigned*>(b + o_status);
+    ws->work_counter = reinterpret_cast<int*>(b + o_work);
+    ws->bytes = off;
+  }
+  return off;
+}
+
+int check_device() {
+  static int state = 0;   // 0 unknown, 1 ok, <0 error
+  if (state == 1) return 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return MEHHUA_E_NODEVICE; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { cuda_fail(e, "cudaGetDeviceProperties"); return MEHHUA_E_NODEVICE; }
+  if (prop.major != 10) {
+    snprintf(g_err, sizeof(g_err), "mehhua kernels are built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    return MEHHUA_E_NODEVICE;
+  }
+  state = 1;
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+struct Prepared {
+  Plan plan;
+  Workspace ws;
+  cudaStream_t stream;
+};
+
+int prepare(const mehhua_config_t* cfg, const mehhua_level_t* levels, int B, bool need_ptrs, void* workspace,
+            size_t workspace_bytes, void* stream, Prepared* out) {
+  int rc = check_device();
+  if (rc) return rc;
+  rc = build_plan(cfg, levels, B, need_ptrs, &out->plan);
+  if (rc) return rc;
+  if (!workspace) return arg_fail("null workspace");
+  if (carve(out->plan, workspace, &out->ws) > workspace_bytes) {
+    snprintf(g_err, sizeof(g_err), "workspace too small: need %zu bytes", out->ws.bytes);
+    return MEHHUA_E_WORKSPACE;
+  }
+  out->stream = static_cast<cudaStream_t>(stream);
+  return 0;
+}
+
+template <int C, int HEAD>
+int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes, const float* scale_factors,
+                    const mehhua_buffers_t* o, cudaStream_t st) {
+  k1a_keys_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(p, ws.keys, o->level_fg);
+  LAUNCHED("k1a_keys_kernel");
+  bool any_topk = false;
+  for (int s = 0; s < p.S; ++s) any_topk |= p.lv[s].topk != 0;
+  if (any_topk) {
+    static bool attr = false;
+    if (!attr) {
+      CU(cudaFuncSetAttribute(k1b_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
+      attr = true;
+    }
+    k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.status);
+    LAUNCHED("k1b_select_kernel");
+  }
+  k1c_gather_kernel<C, HEAD><<<dim3((p.K + kGatherThreads - 1) / kGatherThreads, p.B), kGatherThreads, 0, st>>>(
+      p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
+      o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
+  LAUNCHED("k1c_gather_kernel");
+  return 0;
+}
+
+int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const float* scale_factors,
+              const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!img_shapes || !scale_factors) return arg_fail("null img_shapes / scale_factors");
+  if (!o || !o->score_rows || !o->lam_rows || !o->boxes || !o->topk_idx || !o->row_max || !o->row_argmax ||
+      !o->level_fg)
+    return arg_fail("null K1 output buffer");
+  CU(cudaMemsetAsync(o->level_fg, 0, (size_t)p.B * p.S * sizeof(int), st));
+  CU(cudaMemsetAsync(ws.cand_cnt, 0, (size_t)p.B * sizeof(int), st));
+  CU(cudaMemsetAsync(ws.cand_maxc, 0, (size_t)p.B * sizeof(unsigned), st));
+  if (p.head == MEHHUA_HEAD_RETINA) {
+    switch (p.C) {
+      case 20: return launch_k1_typed<20, MEHHUA_HEAD_RETINA>(p, ws, img_shapes, scale_factors, o, st);
+      case 80: return launch_k1_typed<80, MEHHUA_HEAD_RETINA>(p, ws, img_shapes, scale_factors, o, st);
+      default: return launch_k1_typed<0, MEHHUA_HEAD_RETINA>(p, ws, img_shapes, scale_factors, o, st);
+    }
+  }
+  switch (p.C) {
+    case 21: return launch_k1_typed<21, MEHHUA_HEAD_SSD>(p, ws, img_shapes, scale_factors, o, st);
+    case 81: return launch_k1_typed<81, MEHHUA_HEAD_SSD>(p, ws, img_shapes, scale_factors, o, st);
+    default: return launch_k1_typed<0, MEHHUA_HEAD_SSD>(p, ws, img_shapes, scale_factors, o, st);
+  }
+}
+
+int launch_nms(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!o || !o->boxes || !o->dets || !o->det_labels || !o->det_flat || !o->n_det || !o->n_obj)
+    return arg_fail("null NMS buffer");
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k3a_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
+    attr = true;
+  }
+  k3a_nms_kernel<<<p.B, kNmsThreads, kNmsSmem, st>>>(p, ws.cand, ws.cand_cnt, ws.cand_maxc, o->boxes, o->dets,
+                                                    o->det_labels, o->det_flat, o->n_det, o->n_obj, ws.status);
+  LAUNCHED("k3a_nms_kernel");
+  return 0;
+}
+
+int launch_pairs(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!o || !o->boxes || !o->row_max || !o->row_argmax || !o->lam_rows || !o->level_fg || !o->dets || !o->n_obj ||
+      !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->lam_mean)
+    return arg_fail("null pair buffer");
+  k3b_pairs_kernel<<<p.B, kPairThreads, 0, st>>>(p, o->boxes, o->row_max, o->row_argmax, o->lam_rows, o->level_fg,
+                                                 o->dets, o->n_obj, o->pair_row, o->pair_obj, o->pair_cls,
+                                                 o->pair_off, o->lam_mean, ws.status);
+  LAUNCHED("k3b_pairs_kernel");
+  return 0;
+}
+
+int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, const float* inj,
+              const int64_t* inj_off, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!o || !o->score_rows || !o->lam_rows || !o->lam_mean || !o->pair_row || !o->pair_obj || !o->pair_off ||
+      !o->pair_unc)
+    return arg_fail("null K2 buffer");
+  const size_t smem = k2_smem_bytes(p.C);
+  if (smem > 227 * 1024) return arg_fail("c_out too large for the K2 shared-memory layout");
+  static size_t attr = 0;
+  if (smem > attr) {
+    CU(cudaFuncSetAttribute(k2_dirichlet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  const int per_sm = (int)((227 * 1024) / smem) > 2 ? 2 : ((227 * 1024) / smem >= 1 ? (int)((227 * 1024) / smem) : 1);
+  k2_dirichlet_kernel<<<sm_count() * per_sm, kK2Threads, smem, st>>>(
+      p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off,
+      reinterpret_cast<const long long*>(image_ids), inj, reinterpret_cast<const long long*>(inj_off),
+      o->pair_unc, ws.status);
+  LAUNCHED("k2_dirichlet_kernel");
+  return 0;
+}
+
+int launch_hua(const Plan& p, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!o || !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->pair_unc || !o->n_obj ||
+      !o->image_scores)
+    return arg_fail("null HUA buffer");
+  const size_t smem = (size_t)(kHuaThreads / 32) * p.S * p.C * 8 + MEHHUA_MAX_DETS * 8 + ((p.C + 31) / 32) * 4;
+  if (smem > 227 * 1024) return arg_fail("c_out too large for the K3c shared-memory layout");
+  static size_t attr = 0;
+  if (smem > attr) {
+    CU(cudaFuncSetAttribute(k3c_hua_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  k3c_hua_kernel<<<p.B, kHuaThreads, smem, st>>>(p, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off,
+                                                o->pair_unc, o->n_obj, o->image_scores);
+  LAUNCHED("k3c_hua_kernel");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mehhua_abi_version(void) { return MEHHUA_ABI_VERSION; }
+const char* mehhua_last_cuda_error(void) { return g_err; }
+uint64_t mehhua_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int64_t mehhua_rows_per_image(const mehhua_config_t* cfg, const mehhua_level_t* levels) {
+  Plan p;
+  mehhua_config_t c = *cfg;
+  if (c.pair_cap < 1) c.pair_cap = 1;
+  const int rc = build_plan(&c, levels, 1, false, &p);
+  return rc ? rc : p.K;
+}
+
+size_t mehhua_workspace_bytes(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B) {
+  Plan p;
+  if (build_plan(cfg, levels, B, false, &p)) return 0;
+  return carve(p, nullptr, nullptr);
+}
+
+int mehhua_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace) return arg_fail("null workspace");
+  CU(cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int mehhua_read_status(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B, void* workspace,
+                       void* stream, uint32_t* status_out) {
+  if (!workspace || !status_out) return arg_fail("null status pointer");
+  Plan p;
+  int rc = build_plan(cfg, levels, B, false, &p);
+  if (rc) return rc;
+  Workspace ws;
+  carve(p, workspace, &ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned v = 0;
+  CU(cudaMemcpyAsync(&v, ws.status, sizeof(v), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (v) CU(cudaMemsetAsync(ws.status, 0, sizeof(v), st));
+  *status_out = v;
+  return 0;
+}
+
+int mehhua_k1_alpha_topk(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                         const float* img_shapes, const float* scale_factors, const mehhua_buffers_t* out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  return launch_k1(pr.plan, pr.ws, img_shapes, scale_factors, out, pr.stream);
+}
+
+int mehhua_nms_objects(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                       const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  return launch_nms(pr.plan, pr.ws, out, pr.stream);
+}
+
+int mehhua_iou_pairs(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                     const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  return launch_pairs(pr.plan, pr.ws, out, pr.stream);
+}
+
+int mehhua_k2_dirichlet_epi(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                            const int64_t* image_ids, const float* inj_samples, const int64_t* inj_off,
+                            const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  return launch_k2(pr.plan, pr.ws, image_ids, inj_samples, inj_off, out, pr.stream);
+}
+
+int mehhua_k3_hua(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                  const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  return launch_hua(pr.plan, out, pr.stream);
+}
+
+int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                       const float* img_shapes, const float* scale_factors, const int64_t* image_ids,
+                       const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  if ((rc = launch_k1(pr.plan, pr.ws, img_shapes, scale_factors, out, pr.stream))) return rc;
+  if ((rc = launch_nms(pr.plan, pr.ws, out, pr.stream))) return rc;
+  if ((rc = launch_pairs(pr.plan, pr.ws, out, pr.stream))) return rc;
+  if ((rc = launch_k2(pr.plan, pr.ws, image_ids, nullptr, nullptr, out, pr.stream))) return rc;
+  return launch_hua(pr.plan, out, pr.stream);
+}
+
+size_t mehhua_pool_topk_workspace_bytes(int64_t n) { (void)n; return 256; }
+
+int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k, int64_t* idx_out,
+                        int32_t* n_selected_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!scores || !idx_out || !n_selected_out || !workspace) return arg_fail("null K4 pointer");
+  if (workspace_bytes < 256) return MEHHUA_E_WORKSPACE;
+  if (n < 0 || n > 0x7fffffffll || k < 0) return arg_fail("pool size / k");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k4_pool_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem));
+    attr = true;
+  }
+  k4_pool_topk_kernel<<<1, kPoolThreads, kPoolSmem, st>>>(scores, mask, (long long)n, k,
+                                                         reinterpret_cast<long long*>(idx_out), n_selected_out,
+                                                         static_cast<unsigned*>(workspace));
+  LAUNCHED("k4_pool_topk_kernel");
+  return 0;
+}
+
+// debug / known-answer entry for the Philox block (tests only): out = 4 host uint32
+int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  int rc = check_device();
+  if (rc) return rc;
+  unsigned* d = nullptr;
+  CU(cudaMalloc(&d, 16));
+  philox_kat_kernel<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+  LAUNCHED("philox_kat_kernel");
+  cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer context
+// ---------------------------------------------------------------------------------------------
+struct mehhua_host_ctx {
+  mehhua_config_t cfg;
+  mehhua_level_t shapes[MEHHUA_MAX_LEVELS];
+  mehhua_level_t dev[MEHHUA_MAX_LEVELS];
+  int max_batch;
+  int64_t K;
+  cudaStream_t stream;
+  void* arena;          // one device allocation holding inputs, outputs, workspace
+  size_t arena_bytes;
+  void* workspace;
+  size_t workspace_bytes;
+  unsigned* status;
+  float* img_shapes;
+  float* scale_factors;
+  int64_t* image_ids;
+  mehhua_buffers_t bufs;
+  bool anchors_loaded;
+};
+
+int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* level_shapes, int32_t max_batch,
+                           mehhua_host_ctx_t** ctx_out) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!ctx_out) return arg_fail("null ctx_out");
+  Plan p;
+  if ((rc = build_plan(cfg, level_shapes, max_batch, false, &p))) return rc;
+  mehhua_host_ctx* c = new (std::nothrow) mehhua_host_ctx();
+  if (!c) return arg_fail("out of host memory");
+  c->cfg = *cfg;
+  c->max_batch = max_batch;
+  c->K = p.K;
+  c->anchors_loaded = false;
+  const int B = max_batch, S = p.S, C = p.C, D = p.max_per_img;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  size_t o_log[MEHHUA_MAX_LEVELS], o_del[MEHHUA_MAX_LEVELS], o_lam[MEHHUA_MAX_LEVELS], o_anc[MEHHUA_MAX_LEVELS];
+  for (int s = 0; s < S; ++s) {
+    const size_t n = (size_t)p.lv[s].n;
+    o_log[s] = take((size_t)B * n * C * 4);
+    o_del[s] = take((size_t)B * n * 4 * 4);
+    o_lam[s] = take((size_t)B * n * 4);
+    o_anc[s] = take(n * 16);
+  }
+  const size_t K = (size_t)p.K, PC = (size_t)p.pair_cap;
+  const size_t o_rows = take(B * K * C * 4), o_lamr = take(B * K * 4), o_box = take(B * K * 16);
+  const size_t o_idx = take(B * K * 4), o_rmax = take(B * K * 4), o_rarg = take(B * K * 4);
+  const size_t o_lfg = take((size_t)B * S * 4), o_dets = take((size_t)B * D * 20), o_dl = take((size_t)B * D * 4);
+  const size_t o_df = take((size_t)B * D * 4), o_nd = take((size_t)B * 4), o_no = take((size_t)B * 4);
+  const size_t o_pr = take(B * PC * 4), o_po = take(B * PC * 4), o_pc = take(B * PC * 4);
+  const size_t o_poff = take((size_t)B * (S + 1) * 4), o_lm = take((size_t)B * S * 4), o_pu = take(B * PC * 12);
+  const size_t o_sc = take((size_t)B * 4), o_shp = take((size_t)B * 8), o_sf = take((size_t)B * 16);
+  const size_t o_ids = take((size_t)B * 8);
+  c->workspace_bytes = carve(p, nullptr, nullptr);
+  const size_t o_ws = take(c->workspace_bytes);
+  cudaError_t e = cudaMalloc(&c->arena, off);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc(host ctx arena)"); }
+  c->arena_bytes = off;
+  char* a = static_cast<char*>(c->arena);
+  for (int s = 0; s < S; ++s) {
+    c->shapes[s] = level_shapes[s];
+    c->dev[s] = level_shapes[s];
+    c->dev[s].logits = reinterpret_cast<float*>(a + o_log[s]);
+    c->dev[s].deltas = reinterpret_cast<float*>(a + o_del[s]);
+    c->dev[s].lambda = reinterpret_cast<float*>(a + o_lam[s]);
+    c->dev[s].anchors = reinterpret_cast<float*>(a + o_anc[s]);
+  }
+  mehhua_buffers_t& b = c->bufs;
+  b.score_rows = reinterpret_cast<float*>(a + o_rows);  b.lam_rows = reinterpret_cast<float*>(a + o_lamr);
+  b.boxes = reinterpret_cast<float*>(a + o_box);        b.topk_idx = reinterpret_cast<int32_t*>(a + o_idx);
+  b.row_max = reinterpret_cast<float*>(a + o_rmax);     b.row_argmax = reinterpret_cast<int32_t*>(a + o_rarg);
+  b.level_fg = reinterpret_cast<int32_t*>(a + o_lfg);   b.dets = reinterpret_cast<float*>(a + o_dets);
+  b.det_labels = reinterpret_cast<int32_t*>(a + o_dl);  b.det_flat = reinterpret_cast<int32_t*>(a + o_df);
+  b.n_det = reinterpret_cast<int32_t*>(a + o_nd);       b.n_obj = reinterpret_cast<int32_t*>(a + o_no);
+  b.pair_row = reinterpret_cast<int32_t*>(a + o_pr);    b.pair_obj = reinterpret_cast<int32_t*>(a + o_po);
+  b.pair_cls = reinterpret_cast<int32_t*>(a + o_pc);    b.pair_off = reinterpret_cast<int32_t*>(a + o_poff);
+  b.lam_mean = reinterpret_cast<float*>(a + o_lm);      b.pair_unc = reinterpret_cast<float*>(a + o_pu);
+  b.image_scores = reinterpret_cast<float*>(a + o_sc);
+  c->img_shapes = reinterpret_cast<float*>(a + o_shp);
+  c->scale_factors = reinterpret_cast<float*>(a + o_sf);
+  c->image_ids = reinterpret_cast<int64_t*>(a + o_ids);
+  c->workspace = a + o_ws;
+  Workspace ws;
+  carve(p, c->workspace, &ws);
+  c->status = ws.status;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->workspace, 0, c->workspace_bytes, c->stream);
+  if (e != cudaSuccess) { cudaFree(c->arena); delete c; return cuda_fail(e, "host ctx stream setup"); }
+  *ctx_out = c;
+  return 0;
+}
+
+void mehhua_host_ctx_destroy(mehhua_host_ctx_t* c) {
+  if (!c) return;
+  cudaStreamSynchronize(c->stream);
+  cudaStreamDestroy(c->stream);
+  cudaFree(c->arena);
+  delete c;
+}
+
+int mehhua_score_batch_host(mehhua_host_ctx_t* c, const mehhua_level_t* lh, int32_t B, const float* img_shapes_host,
+                            const float* scale_factors_host, const int64_t* image_ids_host,
+                            float* image_scores_host, uint32_t* status_out) {
+  if (!c || !lh || !img_shapes_host || !scale_factors_host || !image_scores_host) return arg_fail("null host pointer");
+  if (B < 1 || B > c->max_batch) return arg_fail("batch exceeds the context's max_batch");
+  cudaStream_t st = c->stream;
+  const int S = c->cfg.num_levels, C = c->cfg.c_out;
+  for (int s = 0; s < S; ++s) {
+    if (lh[s].H != c->shapes[s].H || lh[s].W != c->shapes[s].W || lh[s].A != c->shapes[s].A)
+      return arg_fail("level geometry differs from the context's");
+    const size_t n = (size_t)lh[s].H * lh[s].W * lh[s].A;
+    if (!lh[s].logits || !lh[s].deltas || !lh[s].lambda) return arg_fail("null host level pointer");
+    CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].logits), lh[s].logits, (size_t)B * n * C * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].deltas), lh[s].deltas, (size_t)B * n * 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].lambda), lh[s].lambda, (size_t)B * n * 4, cudaMemcpyHostToDevice, st));
+    if (lh[s].anchors) {
+      CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].anchors), lh[s].anchors, n * 16, cudaMemcpyHostToDevice, st));
+    } else if (!c->anchors_loaded) {
+      return arg_fail("anchors must be given on the first call");
+    }
+  }
+  c->anchors_loaded = true;
+  CU(cudaMemcpyAsync(c->img_shapes, img_shapes_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->scale_factors, scale_factors_host, (size_t)B * 16, cudaMemcpyHostToDevice, st));
+  const int64_t* ids = nullptr;
+  if (image_ids_host) {
+    CU(cudaMemcpyAsync(c->image_ids, image_ids_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    ids = c->image_ids;
+  }
+  int rc = mehhua_score_batch(&c->cfg, c->dev, B, c->img_shapes, c->scale_factors, ids, &c->bufs, c->workspace,
+                              c->workspace_bytes, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(image_scores_host, c->bufs.image_scores, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  unsigned status = 0;
+  CU(cudaMemcpyAsync(&status, c->status, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (status) CU(cudaMemsetAsync(c->status, 0, 4, st));
+  if (status_out) *status_out = status;
+  return 0;
+}
+
+}  // extern "C"

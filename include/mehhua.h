@@ -1,0 +1,211 @@
+/*
+ * mehhua.h - C ABI of the B200-native MEH alpha -> Dirichlet uncertainty -> HUA -> pool top-k path.
+ *
+ * The reference (MoonLab-YH/AOD_MEH_HUA) has no native plugin layer: its operator API for this
+ * path is a set of Python methods on the MMDetection dense heads.  Each entry point below names
+ * the reference code it replaces (paths relative to /root/reference/mmdet/).  INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every buffer is owned by the caller and pre-allocated at the
+ *     documented upper bound; the only hidden storage is the opaque workspace whose size is
+ *     returned by mehhua_workspace_bytes();
+ *   - device pointers unless the name ends in _host; work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*) and the call returns without synchronising, except the *_host entry points
+ *     and mehhua_read_status();
+ *   - return value 0 = enqueued, negative = MEHHUA_E_* (nothing enqueued);
+ *   - data-dependent failures (capacity overflow) are reported through the status word, read
+ *     with mehhua_read_status(): a dropped batch is never silent (cf. apis/test.py:122-128).
+ *
+ * Layouts: all tensors are dense row-major fp32 / int32.  Level s of a batch holds
+ *   logits [B, A*C_out, H, W]   channel = a*C_out + c      (Lambda_L2.py:266 before permute)
+ *   deltas [B, A*4,     H, W]   channel = a*4 + j          (Lambda_L2.py:278)
+ *   lambda [B, A,       H, W]   relu output of the MEH branch (Lambda_L2.py:96-103, :267)
+ *   anchors[H*W*A, 4]           prior n = (h*W + w)*A + a   (core/anchor/anchor_generator.py:367-378)
+ * K_s = min(N_s, nms_pre) rows per level, concatenated level-major into K_tot rows per image.
+ */
+#ifndef MEHHUA_H_
+#define MEHHUA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEHHUA_ABI_VERSION 1
+#define MEHHUA_MAX_LEVELS 8
+#define MEHHUA_MAX_DETS 256      /* upper bound on max_per_img */
+#define MEHHUA_MAX_NMS_PRE 4096  /* upper bound on nms_pre */
+
+/* error codes (negative return values) */
+#define MEHHUA_E_ARG        (-1)  /* invalid argument / unsupported configuration */
+#define MEHHUA_E_WORKSPACE  (-2)  /* workspace too small */
+#define MEHHUA_E_CUDA       (-3)  /* a CUDA runtime call failed (see mehhua_last_cuda_error) */
+#define MEHHUA_E_NODEVICE   (-4)  /* no CUDA device / wrong architecture */
+
+/* status word bits (mehhua_read_status) */
+#define MEHHUA_ST_PAIR_OVERFLOW   1u  /* an image produced more (box, object) pairs than pair_cap */
+#define MEHHUA_ST_SELECT_SLOWPATH 2u  /* info: a top-k needed extra radix passes (ties / dense bins) */
+#define MEHHUA_ST_BAD_ALPHA       4u  /* info: a Dirichlet alpha <= 0 was met (treated as clamped) */
+
+#define MEHHUA_HEAD_RETINA 0   /* Lambda_L2Net: C_out = C, score = p / (sum(p) + 1e-20 + 1e-9) */
+#define MEHHUA_HEAD_SSD    1   /* MyLSSDHead:   C_out = C + 1 (background last), score = p     */
+
+#define MEHHUA_AGG_SUM 0
+#define MEHHUA_AGG_AVG 1
+#define MEHHUA_AGG_MAX 2
+
+typedef struct mehhua_level {
+  const float* logits;
+  const float* deltas;
+  const float* lambda;
+  const float* anchors;
+  int32_t H, W, A;
+  int32_t reserved;
+} mehhua_level_t;
+
+/* Constants of the path; defaults = the reference's hard-coded values. */
+typedef struct mehhua_config {
+  int32_t head;            /* MEHHUA_HEAD_* */
+  int32_t c_out;           /* cls_out_channels */
+  int32_t num_levels;
+  int32_t nms_pre;         /* test_cfg.nms_pre (1000); <= 0 disables the per-level top-k */
+  float   score_thr;       /* test_cfg.score_thr: 0.05 Retina / 0.02 SSD, strict > */
+  float   nms_iou;         /* test_cfg.nms.iou_threshold 0.5, strict > */
+  int32_t max_per_img;     /* test_cfg.max_per_img 100 / 200 */
+  float   fg_thr;          /* 0.3  Lambda_L2.py:500,508 */
+  float   obj_thr;         /* 0.3  Lambda_L2.py:349 */
+  float   cluster_iou;     /* 0.5  Lambda_L2.py:349 */
+  float   lambda_scale;    /* 25   Lambda_L2.py:515 */
+  float   lambda_eps;      /* 1e-7 Lambda_L2.py:514 */
+  int32_t use_lambda;      /* 1; 0 = Lambda_L2_noL.py:531 */
+  int32_t n_samples;       /* 500  Lambda_L2.py:520 */
+  int32_t agg_object, agg_scale, agg_class;  /* MEHHUA_AGG_*; 'objectSum_scaleMax_classSum' */
+  int32_t cls_w;           /* clsW: multiply by the number of distinct classes (Lambda_L2.py:617) */
+  float   means[4];        /* bbox_coder target_means */
+  float   stds[4];         /* bbox_coder target_stds  */
+  float   wh_ratio_clip;   /* 16/1000 */
+  int32_t rescale;         /* divide boxes by scale_factor (Lambda_L2.py:307-308) */
+  int32_t pair_cap;        /* capacity of the per-image pair list */
+  int32_t reserved;
+  uint64_t seed;           /* Philox key of the free-running sampler */
+} mehhua_config_t;
+
+/* Caller-owned result buffers.  K_tot = sum_s K_s, S = num_levels, D = max_per_img. */
+typedef struct mehhua_buffers {
+  float*   score_rows;   /* [B, K_tot, C_out]  scores of the kept priors (Lambda_L2.py:295)       */
+  float*   lam_rows;     /* [B, K_tot]         their lambda (Lambda_L2.py:297)                    */
+  float*   boxes;        /* [B, K_tot, 4]      decoded, clipped, rescaled (Lambda_L2.py:299-308)  */
+  int32_t* topk_idx;     /* [B, K_tot]         prior index inside its level (Lambda_L2.py:290)    */
+  float*   row_max;      /* [B, K_tot]         max_c score (incl. background for SSD)             */
+  int32_t* row_argmax;   /* [B, K_tot]         argmax_c score (Lambda_L2.py:526)                  */
+  int32_t* level_fg;     /* [B, S]             any(max_c softmax > fg_thr) (Lambda_L2.py:496-502) */
+  float*   dets;         /* [B, D, 5]          x1,y1,x2,y2,score in descending score              */
+  int32_t* det_labels;   /* [B, D]                                                                */
+  int32_t* det_flat;     /* [B, D]             row*C + class of each detection                    */
+  int32_t* n_det;        /* [B]                                                                   */
+  int32_t* n_obj;        /* [B]                detections with score > obj_thr                    */
+  int32_t* pair_row;     /* [B, pair_cap]      row (0..K_tot) of each (box, object) pair          */
+  int32_t* pair_obj;     /* [B, pair_cap]      object index                                       */
+  int32_t* pair_cls;     /* [B, pair_cap]      argmax class of the row                            */
+  int32_t* pair_off;     /* [B, S+1]           first pair of each level; [S] = pairs of the image */
+  float*   lam_mean;     /* [B, S]             mean lambda over the level's pairs                 */
+  float*   pair_unc;     /* [B, pair_cap, 3]   total, aleatoric, epistemic (Lambda_L2.py:521-525) */
+  float*   image_scores; /* [B]                AggregateObjScaleUnc output                        */
+} mehhua_buffers_t;
+
+int         mehhua_abi_version(void);
+const char* mehhua_last_cuda_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches counter) */
+uint64_t    mehhua_launch_count(void);
+
+/* rows per image after the per-level top-k (K_tot) for a geometry; levels' pointers are ignored */
+int64_t mehhua_rows_per_image(const mehhua_config_t* cfg, const mehhua_level_t* levels);
+size_t  mehhua_workspace_bytes(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B);
+/* zero the workspace once after allocating it (counters and the status word live there) */
+int     mehhua_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+/* blocking: OR of MEHHUA_ST_* bits accumulated in the workspace since the last read; clears them.
+ * cfg / levels / B must be the ones the workspace is used with (they fix the status word's offset) */
+int     mehhua_read_status(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                           void* workspace, void* stream, uint32_t* status_out);
+
+/* K1: fused logits -> softmax/score -> ranking key -> per-level top-k -> gather rows / lambda /
+ * decoded boxes (+ level-FG flags, NMS candidates).  Replaces the per-level block of
+ * _get_bboxes (Lambda_L2.py:264-326, My_L_ssd_head.py:325-361), delta2bbox
+ * (core/bbox/coder/delta_xywh_bbox_coder.py:205-267) and the second softmax pass of
+ * ComputeObjUnc (Lambda_L2.py:496-502).
+ * img_shapes [B,2] = (H, W) used for clipping; scale_factors [B,4]. */
+int mehhua_k1_alpha_topk(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                         const float* img_shapes, const float* scale_factors,
+                         const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* K3a: multi-class NMS -> detections and objects.  Replaces multiclass_nms
+ * (core/post_processing/bbox_nms.py:7-93 -> mmcv batched_nms) and the det[:, -1] > 0.3 filter of
+ * GetObjectIdx (Lambda_L2.py:344).  Needs K1's outputs in `out` and its workspace. */
+int mehhua_nms_objects(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                       const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* K3b: IoU clustering of kept boxes onto objects -> ordered pair list.  Replaces GetObjectIdx /
+ * bbox_overlaps (Lambda_L2.py:343-349, iou2d_calculator.py:206-252) and the mask / nonzero /
+ * lambda-mean prologue of ComputeObjUnc (Lambda_L2.py:503-515). */
+int mehhua_iou_pairs(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                     const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* K2: alpha = score * lambda', T Dirichlet samples per pair kept in registers / shared memory,
+ * -> total / aleatoric / epistemic per pair.  Replaces Lambda_L2.py:517-525.
+ * image_ids [B] (device, may be NULL = 0..B-1) key the Philox streams by global image id.
+ * inj_samples (may be NULL): the oracle's drawn samples, one [T, P_bs, C_out] block per
+ * (image, level) at element offset inj_off[b*S + s] (device int64, -1 = no block); when given
+ * the kernel consumes them instead of drawing. */
+int mehhua_k2_dirichlet_epi(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                            const int64_t* image_ids, const float* inj_samples,
+                            const int64_t* inj_off, const mehhua_buffers_t* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* K3c: segmented means keyed by (object, level, class) and the bottom-up class -> level ->
+ * object aggregation.  Replaces Lambda_L2.py:526-536 and AggregateObjScaleUnc (:597-619). */
+int mehhua_k3_hua(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                  const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* The whole per-batch path K1 -> K3a -> K3b -> K2 -> K3c on one stream, no host sync.
+ * Replaces the Entropy_NMS route of _get_bboxes (Lambda_L2.py:254-384). */
+int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                       const float* img_shapes, const float* scale_factors,
+                       const int64_t* image_ids, const mehhua_buffers_t* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* K4: indices of the k largest scores among candidates (mask[i] != 0; mask may be NULL), written
+ * in descending score order (ties: larger index first, the order a stable ascending argsort
+ * followed by [-k:] would keep).  Replaces the arg[-nonZeroSize:] part of update_X_L
+ * (utils/active_datasets.py:106-107, 124).  n_selected_out (device int32) = min(k, #candidates). */
+size_t mehhua_pool_topk_workspace_bytes(int64_t n);
+int    mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k,
+                           int64_t* idx_out, int32_t* n_selected_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* Known-answer hook for the Philox4x32-10 block of K2 (tests): ctr[4], key[2] -> out[4], host arrays. */
+int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Host-buffer entry point: same as mehhua_score_batch but every pointer in `levels`, img_shapes,
+ * scale_factors, image_ids and image_scores_host is HOST memory.  The call copies the inputs to
+ * the device (pinned staging inside the handle), scores them and copies the B image scores back;
+ * it blocks until image_scores_host is valid.  Handle = resident device buffers for one geometry. */
+typedef struct mehhua_host_ctx mehhua_host_ctx_t;
+int  mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* level_shapes,
+                            int32_t max_batch, mehhua_host_ctx_t** ctx_out);
+void mehhua_host_ctx_destroy(mehhua_host_ctx_t* ctx);
+int  mehhua_score_batch_host(mehhua_host_ctx_t* ctx, const mehhua_level_t* levels_host, int32_t B,
+                             const float* img_shapes_host, const float* scale_factors_host,
+                             const int64_t* image_ids_host, float* image_scores_host,
+                             uint32_t* status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MEHHUA_H_ */

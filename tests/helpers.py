@@ -1,0 +1,60 @@
+"""Shared test plumbing: seeded batches, oracle runs with captured Dirichlet samples."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from aod_meh_hua_b200.specs import ScoringParams, get_spec
+from aod_meh_hua_b200.synth import SyntheticPool
+from oracle import meh_hua_oracle as O
+
+
+def make_batch(spec_name: str, gids, seed0: int = 20, scale_factor=(1.0, 1.0, 1.0, 1.0)):
+    spec = get_spec(spec_name)
+    pool = SyntheticPool(spec, seed0=seed0, device="cpu", scale_factor=scale_factor)
+    return spec, pool.batch(list(gids))
+
+
+class Recorder:
+    """Sampler hook: draws with torch (seeded) and keeps alpha + samples per (image, level)."""
+
+    def __init__(self, seed: int = 1234):
+        self.gen_seed = seed
+        self.blocks = {}
+        torch.manual_seed(seed)
+
+    def __call__(self, alpha, T, i, s):
+        smp = O.default_sampler(alpha, T, i, s)
+        self.blocks[(i, s)] = (alpha.clone(), smp)
+        return smp
+
+
+def run_oracle(spec, batch, params: ScoringParams = None, seed: int = 1234):
+    params = params or ScoringParams()
+    rec = Recorder(seed)
+    out = O.score_batch(batch, sampler=rec, **O.spec_kwargs(spec, params))
+    return out, rec
+
+
+def injection_buffers(spec, rec: Recorder, B: int, device):
+    """Flat sample buffer + per-(image, level) element offsets for mehhua_k2_dirichlet_epi."""
+    S = spec.num_levels
+    off = np.full(B * S, -1, dtype=np.int64)
+    chunks, pos = [], 0
+    for (i, s), (_, smp) in sorted(rec.blocks.items()):
+        off[i * S + s] = pos
+        chunks.append(smp.reshape(-1))
+        pos += smp.numel()
+    flat = torch.cat(chunks) if chunks else torch.zeros(1)
+    return flat.to(device), torch.from_numpy(off).to(device)
+
+
+def oracle_pairs(out, b: int):
+    """Ordered (row, obj, cls, total, ale, epi) arrays of image b from the oracle's flat dump."""
+    recs = [r for r in out["flat"] if r["image"] == b]
+    recs.sort(key=lambda r: r["level"])
+    if not recs:
+        z = np.zeros(0)
+        return z.astype(np.int64), z.astype(np.int64), z.astype(np.int64), z, z, z, []
+    cat = lambda k: np.concatenate([r[k] for r in recs])
+    return cat("row"), cat("obj"), cat("cls"), cat("total"), cat("ale"), cat("epi"), recs

@@ -1,0 +1,167 @@
+"""GPU parity: every stage of the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Integer decisions (top-k membership and order, level-FG flags, NMS keep list,
+pair list, class keys) are compared exactly; floats within rel 1e-5 (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from aod_meh_hua_b200.scoring import Scorer
+from aod_meh_hua_b200.specs import HEAD_RETINA, ScoringParams
+from tests.helpers import injection_buffers, make_batch, oracle_pairs, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+CASES = [
+    ("tiny_retina_voc", [0, 1], (1.0, 1.0, 1.0, 1.0)),
+    ("tiny_retina_coco", [0, 1, 2], (1.0, 1.0, 1.0, 1.0)),
+    ("tiny_ssd_voc", [0, 1], (1.0, 1.0, 1.0, 1.0)),
+    ("tiny_retina_coco", [3, 4], (1.07, 0.94, 1.07, 0.94)),
+]
+
+
+def _run(spec_name, gids, sf, params=None):
+    spec, batch = make_batch(spec_name, gids, scale_factor=sf)
+    params = params or ScoringParams()
+    out, rec = run_oracle(spec, batch, params)
+    sc = Scorer(spec, params, max_batch=len(gids), device="cuda:0")
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    sc.k1()
+    sc.nms()
+    sc.pairs()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off)
+    sc.hua()
+    torch.cuda.synchronize()
+    st = sc.check_status()
+    res = sc.result()
+    return spec, batch, out, rec, res, st
+
+
+@pytest.mark.parametrize("spec_name,gids,sf", CASES)
+def test_stagewise_parity(spec_name, gids, sf):
+    spec, batch, out, rec, res, st = _run(spec_name, gids, sf)
+    B, S, C = len(gids), spec.num_levels, spec.c_out
+    koff = np.concatenate([[0], np.cumsum(spec.level_k)])
+
+    # --- K1: per-level top-k index order, rows, lambda, boxes, level-FG flags
+    idx = res.topk_idx.cpu().numpy()
+    for s in range(S):
+        want = out["lvl_idx"][s].numpy()
+        got = idx[:, koff[s]:koff[s + 1]]
+        assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1)), f"level {s}: top-k set differs"
+        assert np.array_equal(got, want), f"level {s}: top-k order differs"
+    np.testing.assert_allclose(res.score_rows.cpu().numpy(), out["scores"].numpy(), rtol=RTOL, atol=1e-9)
+    np.testing.assert_array_equal(res.lam_rows.cpu().numpy(), torch.cat(out["lvl_L"], dim=1).numpy())
+    np.testing.assert_allclose(res.boxes.cpu().numpy(), out["boxes"].numpy(), rtol=RTOL, atol=1e-4)
+    np.testing.assert_array_equal(res.level_fg.cpu().numpy().astype(bool), out["level_fg"])
+    np.testing.assert_array_equal(res.row_argmax.cpu().numpy(), out["scores"].argmax(dim=2).numpy())
+
+    # --- K3a: detections (kept set, order, labels), object count
+    n_det = res.n_det.cpu().numpy()
+    n_obj = res.n_obj.cpu().numpy()
+    for b in range(B):
+        d_want, l_want = out["dets"][b].numpy(), out["labels"][b].numpy()
+        assert n_det[b] == len(d_want)
+        assert np.array_equal(res.det_flat[b, :n_det[b]].cpu().numpy(), out["det_flat"][b].numpy())
+        assert np.array_equal(res.det_labels[b, :n_det[b]].cpu().numpy(), l_want)
+        np.testing.assert_allclose(res.dets[b, :n_det[b]].cpu().numpy(), d_want, rtol=RTOL, atol=1e-4)
+        assert n_obj[b] == int((d_want[:, 4] > 0.3).sum())
+
+    # --- K3b: ordered pair list, class keys, lambda means
+    poff = res.pair_off.cpu().numpy()
+    for b in range(B):
+        row, obj, cls, tot, ale, epi, recs = oracle_pairs(out, b)
+        n = poff[b, S]
+        assert n == len(row)
+        assert np.array_equal(res.pair_row[b, :n].cpu().numpy(), row)
+        assert np.array_equal(res.pair_obj[b, :n].cpu().numpy(), obj)
+        assert np.array_equal(res.pair_cls[b, :n].cpu().numpy(), cls)
+        # --- K2 with the oracle's samples injected
+        unc = res.pair_unc[b, :n].cpu().numpy()
+        np.testing.assert_allclose(unc[:, 0], tot, rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(unc[:, 1], ale, rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(unc[:, 2], epi, rtol=1e-4, atol=5e-6)
+
+    # --- K3c: image scores
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(),
+                               np.asarray(out["image_scores"], dtype=np.float32), rtol=RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("agg", ["objectSum_scaleMax_classSum", "objectAvg_scaleSum_classMax",
+                                 "objectMax_scaleAvg_classAvg"])
+def test_aggregation_matrix(agg):
+    params = ScoringParams(agg=agg, cls_w=(agg != "objectSum_scaleMax_classSum"))
+    spec, batch, out, rec, res, st = _run("tiny_retina_coco", [0, 1, 2], (1.0, 1.0, 1.0, 1.0), params)
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(),
+                               np.asarray(out["image_scores"], dtype=np.float32), rtol=RTOL, atol=1e-5)
+
+
+def test_free_running_sampler_matches_closed_form():
+    """Philox/Marsaglia-Tsang sampler: per-pair total / aleatoric against the Dirichlet closed forms
+    (SURVEY 7 'sampling parity').  MC error at T samples is O(1/sqrt(T)); use a large T."""
+    from oracle import meh_hua_oracle as O
+    params = ScoringParams(n_samples=20000)
+    spec, batch = make_batch("tiny_retina_coco", [0, 1, 2])
+    oracle_params = ScoringParams(n_samples=8)
+    out, rec = run_oracle(spec, batch, oracle_params)
+    sc = Scorer(spec, params, max_batch=3, device="cuda:0")
+    res = sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                   batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    torch.cuda.synchronize()
+    poff = res.pair_off.cpu().numpy()
+    S = spec.num_levels
+    checked = 0
+    for b in range(3):
+        row, obj, cls, _, _, _, recs = oracle_pairs(out, b)
+        n = poff[b, S]
+        assert n == len(row)
+        if n == 0:
+            continue
+        alpha = np.concatenate([r["alpha"] for r in recs]).astype(np.float64)
+        h, e_ent, epi_inf = O.dirichlet_expectations(alpha)
+        unc = res.pair_unc[b, :n].cpu().numpy().astype(np.float64)
+        # aleatoric is an unbiased MC mean; total is H(mean) with O(C/T) bias
+        np.testing.assert_allclose(unc[:, 1], e_ent, rtol=0.05, atol=5e-3)
+        np.testing.assert_allclose(unc[:, 0], h, rtol=0.05, atol=5e-3)
+        checked += n
+    assert checked > 0
+
+
+def test_philox_known_answers():
+    import ctypes as C
+    from aod_meh_hua_b200 import _lib
+    lib = _lib.load()
+    kats = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in kats:
+        out = (C.c_uint32 * 4)()
+        _lib.check(lib.mehhua_debug_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out), "philox")
+        assert tuple(out) == want
+
+
+def test_pool_topk_matches_stable_argsort():
+    from aod_meh_hua_b200.scoring import pool_topk
+    g = torch.Generator().manual_seed(5)
+    n = 100_000
+    scores = torch.rand(n, generator=g)
+    scores[torch.rand(n, generator=g) < 0.3] = 0.0          # many exact ties at zero
+    scores[1000:1010] = scores[5]                           # a tie group above zero
+    mask = (torch.rand(n, generator=g) < 0.8)
+    for k in (1, 413, 2500, 9000):
+        got = pool_topk(scores.cuda(), k, mask.cuda()).cpu().numpy()
+        cand = np.nonzero(mask.numpy())[0]
+        order = np.argsort(scores.numpy()[cand], kind="stable")
+        want = cand[order[-k:]][::-1]
+        assert np.array_equal(got, want)
+    # fewer candidates than k
+    few = torch.zeros(n, dtype=torch.bool)
+    few[[3, 77, 9000]] = True
+    got = pool_topk(scores.cuda(), 10, few.cuda()).cpu().numpy()
+    assert sorted(got.tolist()) == [3, 77, 9000]
