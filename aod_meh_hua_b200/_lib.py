@@ -70,6 +70,8 @@ SYMBOLS = {
     "mehhua_k2_dirichlet_epi": (C.c_int, [_CFG, _LV, C.c_int32, _P, _P, _P, _BUF, _P, C.c_size_t, _P]),
     "mehhua_k3_hua": (C.c_int, [_CFG, _LV, C.c_int32, _BUF, _P, C.c_size_t, _P]),
     "mehhua_score_batch": (C.c_int, [_CFG, _LV, C.c_int32, _P, _P, _P, _BUF, _P, C.c_size_t, _P]),
+    "mehhua_stage_timing_begin": (C.c_int, [C.c_int32]),
+    "mehhua_stage_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mehhua_pool_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "mehhua_k4_pool_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "mehhua_debug_philox": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "k1_alpha_topk.cuh"
@@ -41,6 +42,19 @@ int arg_fail(const char* what) {
   } while (0)
 
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Optional per-stage CUDA-event timing of mehhua_score_batch (bench.py's live roofline numbers).
+constexpr int kStages = 7;   // K1a, K1b, K1c, K3a, K3b, K2, K3c
+struct StageTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // (kStages + 1) events per recorded call
+  size_t calls = 0, max_calls = 0;
+} g_timer;
+
+void timer_mark(cudaStream_t st, int slot) {
+  if (!g_timer.on || g_timer.calls >= g_timer.max_calls) return;
+  cudaEventRecord(g_timer.ev[g_timer.calls * (kStages + 1) + slot], st);
+}
 
 int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool need_ptrs, Plan* out) {
   if (!cfg || !lv) return arg_fail("null config / levels");
@@ -167,8 +181,10 @@ int prepare(const mehhua_config_t* cfg, const mehhua_level_t* levels, int B, boo
 template <int C, int HEAD>
 int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes, const float* scale_factors,
                     const mehhua_buffers_t* o, cudaStream_t st) {
+  timer_mark(st, 0);
   k1a_keys_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(p, ws.keys, o->level_fg);
   LAUNCHED("k1a_keys_kernel");
+  timer_mark(st, 1);
   bool any_topk = false;
   for (int s = 0; s < p.S; ++s) any_topk |= p.lv[s].topk != 0;
   if (any_topk) {
@@ -180,6 +196,7 @@ int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes,
     k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.status);
     LAUNCHED("k1b_select_kernel");
   }
+  timer_mark(st, 2);
   k1c_gather_kernel<C, HEAD><<<dim3((p.K + kGatherThreads - 1) / kGatherThreads, p.B), kGatherThreads, 0, st>>>(
       p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
       o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
@@ -367,10 +384,48 @@ int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels,
   int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
   if (rc) return rc;
   if ((rc = launch_k1(pr.plan, pr.ws, img_shapes, scale_factors, out, pr.stream))) return rc;
+  timer_mark(pr.stream, 3);
   if ((rc = launch_nms(pr.plan, pr.ws, out, pr.stream))) return rc;
+  timer_mark(pr.stream, 4);
   if ((rc = launch_pairs(pr.plan, pr.ws, out, pr.stream))) return rc;
+  timer_mark(pr.stream, 5);
   if ((rc = launch_k2(pr.plan, pr.ws, image_ids, nullptr, nullptr, out, pr.stream))) return rc;
-  return launch_hua(pr.plan, out, pr.stream);
+  timer_mark(pr.stream, 6);
+  rc = launch_hua(pr.plan, out, pr.stream);
+  timer_mark(pr.stream, 7);
+  if (g_timer.on && g_timer.calls < g_timer.max_calls) ++g_timer.calls;
+  return rc;
+}
+
+int mehhua_stage_timing_begin(int32_t max_calls) {
+  if (max_calls < 1 || max_calls > 100000) return arg_fail("max_calls");
+  for (cudaEvent_t e : g_timer.ev) cudaEventDestroy(e);
+  g_timer.ev.assign((size_t)max_calls * (kStages + 1), nullptr);
+  for (auto& e : g_timer.ev) CU(cudaEventCreate(&e));
+  g_timer.calls = 0;
+  g_timer.max_calls = (size_t)max_calls;
+  g_timer.on = true;
+  return 0;
+}
+
+int mehhua_stage_timing_end(double* ms_sum, int32_t* calls_out) {
+  if (!ms_sum || !calls_out) return arg_fail("null timing output");
+  g_timer.on = false;
+  for (int i = 0; i < kStages; ++i) ms_sum[i] = 0.0;
+  for (size_t c = 0; c < g_timer.calls; ++c) {
+    cudaEvent_t* e = &g_timer.ev[c * (kStages + 1)];
+    CU(cudaEventSynchronize(e[kStages]));
+    for (int i = 0; i < kStages; ++i) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+      ms_sum[i] += ms;
+    }
+  }
+  *calls_out = (int32_t)g_timer.calls;
+  for (cudaEvent_t e : g_timer.ev) cudaEventDestroy(e);
+  g_timer.ev.clear();
+  g_timer.calls = g_timer.max_calls = 0;
+  return 0;
 }
 
 size_t mehhua_pool_topk_workspace_bytes(int64_t n) { (void)n; return 256; }

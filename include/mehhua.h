@@ -180,6 +180,15 @@ int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels,
                        const int64_t* image_ids, const mehhua_buffers_t* out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Optional live timing of mehhua_score_batch's stages with CUDA events recorded on the call's own
+ * stream (used by bench.py for the roofline numbers).  _begin arms it for up to max_calls calls;
+ * _end blocks, writes the summed milliseconds of the 7 stages
+ * {K1a keys, K1b select, K1c gather, K3a nms, K3b pairs, K2 sampler, K3c hua} and the number of
+ * recorded calls, and disarms it.  Not thread-safe; one timed stream at a time. */
+#define MEHHUA_NUM_STAGES 7
+int mehhua_stage_timing_begin(int32_t max_calls);
+int mehhua_stage_timing_end(double* ms_sum, int32_t* calls_out);
+
 /* K4: indices of the k largest scores among candidates (mask[i] != 0; mask may be NULL), written
  * in descending score order (ties: larger index first, the order a stable ascending argsort
  * followed by [-k:] would keep).  Replaces the arg[-nonZeroSize:] part of update_X_L

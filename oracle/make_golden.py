@@ -1,0 +1,196 @@
+"""Mint golden vectors by running the REFERENCE'S OWN functions (build container only).
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+The reference has no fixtures for this path, so the goldens are outputs of its own
+`_get_bboxes` -> `ComputeObjUnc` -> `AggregateObjScaleUnc`, `delta2bbox`, anchor generators and
+`update_X_L`, AST-loaded unmodified from /root/reference (oracle/ref_loader.py) and executed on
+seeded synthetic head outputs (aod_meh_hua_b200/synth.py).  Inputs are NOT stored: tests regenerate
+them from the seed and verify a checksum.  Dirichlet draws come from torch's CPU generator seeded
+with `sample_seed`; alpha per (image, level) and every derived value are stored.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+from torch.distributions import Dirichlet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from aod_meh_hua_b200.specs import HEAD_RETINA, get_spec  # noqa: E402
+from aod_meh_hua_b200.synth import SyntheticPool  # noqa: E402
+from aod_meh_hua_b200 import anchors as my_anchors  # noqa: E402
+from oracle import ref_loader as RL  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+CASES = [
+    # name, spec, image ids, pool seed, sample seed, scale factor, uPool2, clsW
+    ("retina_voc", "tiny_retina_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
+    ("retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
+    ("retina_coco_aniso", "tiny_retina_coco", [3, 4], 20, 99, (1.07, 0.94, 1.07, 0.94), "objectAvg_scaleSum_classMax", True),
+    ("ssd_voc", "tiny_ssd_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
+]
+
+
+def batch_checksum(batch) -> str:
+    h = hashlib.sha256()
+    for key in ("cls_scores", "bbox_preds", "L_scores", "anchors"):
+        for t in batch[key]:
+            h.update(t.contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def run_reference_case(spec_name, gids, pool_seed, sample_seed, sf, upool2, clsw):
+    spec = get_spec(spec_name)
+    batch = SyntheticPool(spec, seed0=pool_seed, scale_factor=sf).batch(gids)
+    kind = "retina" if spec.head == HEAD_RETINA else "ssd"
+    head = RL.make_head(kind, spec.c_out, spec.target_stds, spec.score_thr, spec.max_per_img, spec.nms_pre,
+                        spec.nms_iou)
+    rec = []
+
+    class RecordingDirichlet:
+        def __init__(self, alpha):
+            self.alpha = alpha
+            self.dist = Dirichlet(alpha)
+
+        def sample(self, n):
+            s = self.dist.sample(n)
+            rec.append((self.alpha.clone(), s))
+            return s
+
+    head._fn_globals["Dirichlet"] = RecordingDirichlet
+    captured = {}
+    real_compute = head.ComputeObjUnc
+
+    def compute_spy(*a, **k):
+        captured["pos_bboxes"] = [p.clone() for p in a[1]]
+        captured["nested"] = real_compute(*a, **k)
+        return captured["nested"]
+
+    head.ComputeObjUnc = compute_spy
+    kw = dict(isUnc="Epistemic", uPool="Entropy_NMS", uPool2=upool2, L_scores=batch["L_scores"], isEval=False,
+              showNMS=False, saveUnc=False, saveMaxConf=False, clsW=clsw, scaleUnc=False, score_thr=0.3,
+              iou_thr=0.9, batchIdx=0, return_box=False)
+    torch.manual_seed(sample_seed)
+    dets, unc = head._get_bboxes(batch["cls_scores"], batch["bbox_preds"], batch["anchors"], batch["img_shapes"],
+                                 [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]], None, True, True,
+                                 **kw)
+    g = dict(checksum=np.frombuffer(bytes.fromhex(batch_checksum(batch)), dtype=np.uint8),
+             image_scores=np.asarray(unc, dtype=np.float64), n_images=np.int64(len(gids)))
+    for b, (d, l) in enumerate(dets):
+        g[f"dets_{b}"] = d.numpy()
+        g[f"labels_{b}"] = l.numpy()
+        g[f"pos_nz_{b}"] = captured["pos_bboxes"][b].nonzero().numpy().astype(np.int32)
+        g[f"pos_shape_{b}"] = np.asarray(captured["pos_bboxes"][b].shape, dtype=np.int64)
+    groups = []
+    for b, img in enumerate(captured["nested"]):
+        for o, obj in enumerate(img):
+            for s, lvl in enumerate(obj):
+                for c, (ale, epi) in lvl.items():
+                    groups.append((b, o, s, int(c), float(ale), float(epi)))
+    g["groups"] = np.asarray(groups, dtype=np.float64).reshape(-1, 6)
+    h = hashlib.sha256()
+    for k, (alpha, smp) in enumerate(rec):
+        g[f"alpha_{k}"] = alpha.numpy()
+        h.update(smp.numpy().tobytes())
+    g["n_blocks"] = np.int64(len(rec))
+    g["samples_sha256"] = np.frombuffer(h.digest(), dtype=np.uint8)
+    if rec:  # one small block of raw samples so injection can be tested without torch's RNG
+        k = int(np.argmin([a.shape[0] for a, _ in rec]))
+        g["sample_block_index"] = np.int64(k)
+        g["sample_block"] = rec[k][1].numpy()
+    return g
+
+
+def kat_goldens():
+    ns = RL.base_namespace()
+    g = {}
+    # docstring known-answer of delta2bbox (delta_xywh_bbox_coder.py:190-203)
+    rois = torch.Tensor([[0., 0., 1., 1.], [0., 0., 1., 1.], [0., 0., 1., 1.], [5., 5., 5., 5.]])
+    deltas = torch.Tensor([[0., 0., 0., 0.], [1., 1., 1., 1.], [0., 0., 2., -1.], [0.7, -1.9, -0.5, 0.3]])
+    g["d2b_rois"], g["d2b_deltas"] = rois.numpy(), deltas.numpy()
+    g["d2b_out"] = ns["delta2bbox"](rois, deltas, max_shape=(32, 32, 3)).numpy()
+    # seeded random decode incl. clamping and clipping, SSD stds
+    gen = torch.Generator().manual_seed(7)
+    r = torch.rand(64, 2, generator=gen) * 200
+    rois2 = torch.cat([r, r + torch.rand(64, 2, generator=gen) * 100 + 1], dim=1)
+    d2 = torch.randn(64, 4, generator=gen) * 3
+    g["d2b2_rois"], g["d2b2_deltas"] = rois2.numpy(), d2.numpy()
+    g["d2b2_out"] = ns["delta2bbox"](rois2, d2, (0., 0., 0., 0.), (0.1, 0.1, 0.2, 0.2), (120, 160, 3)).numpy()
+    # bbox_overlaps on seeded boxes (+ empty second operand)
+    b1, b2 = rois2[:40], rois2[30:]
+    g["iou_b1"], g["iou_b2"] = b1.numpy(), b2.numpy()
+    g["iou_out"] = ns["bbox_overlaps"](b1, b2).numpy()
+    g["iou_empty_shape"] = np.asarray(ns["bbox_overlaps"](b1, b2[:0]).shape, dtype=np.int64)
+    # anchors: reference generators vs this repo's, per named config (stored as checksums)
+    AG, SAG = RL.load_anchor_generators()
+    import warnings
+    for name in ("cfg1_retina_r50_512_voc", "cfg2_ssd300_voc", "cfg3_retina_r50_800x1344_coco", "cfg4_ssd512_coco",
+                 "tiny_retina_voc", "tiny_ssd_voc"):
+        spec = get_spec(name)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if spec.head == HEAD_RETINA:
+                gen_ = AG(strides=list(spec.strides), ratios=list(spec.retina_ratios),
+                          octave_base_scale=spec.retina_octave_base_scale,
+                          scales_per_octave=spec.retina_scales_per_octave)
+            else:
+                gen_ = SAG(strides=list(spec.strides), ratios=[list(r) for r in spec.ssd_ratios],
+                           basesize_ratio_range=spec.ssd_ratio_range, input_size=spec.ssd_input_size,
+                           scale_major=False)
+            ref = gen_.grid_anchors(list(spec.featmaps), device="cpu")
+        mine = my_anchors.grid_anchors(spec)
+        h = hashlib.sha256()
+        for r_, m_ in zip(ref, mine):
+            assert torch.equal(r_, m_), f"{name}: anchors differ from the reference generator"
+            h.update(r_.numpy().tobytes())
+        g[f"anchors_sha256_{name}"] = np.frombuffer(h.digest(), dtype=np.uint8)
+    # docstring known-answer of AnchorGenerator (anchor_generator.py:41-57)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g["anchor_kat"] = AG([16], [1.], [1.], [9]).grid_anchors([(2, 2)], device="cpu")[0].numpy()
+    # ExtractAggFunc tokens
+    import torch as _t
+    names = {_t.sum: 0, _t.mean: 1, _t.max: 2}
+    for spec_str in ("objectSum_scaleMax_classSum", "objectAvg_scaleSum_classMax", "objectMax_scaleAvg_classAvg"):
+        f = ns["ExtractAggFunc"](spec_str)
+        g[f"agg_{spec_str}"] = np.asarray([names[f["object"]], names[f["scale"]], names[f["class"]]], dtype=np.int64)
+    # update_X_L on a seeded pool with exact zeros (utils/active_datasets.py:102-135)
+    rs = np.random.RandomState(3)
+    n = 2000
+    unc = rs.rand(n).astype(np.float32)
+    unc[rs.rand(n) < 0.25] = 0.0
+    X_all = np.arange(n)
+    X_L = np.sort(rs.choice(n, 100, replace=False))
+    np.random.seed(11)
+    xl, xu = ns["update_X_L"](unc.copy(), X_all, X_L.copy(), 80, zeroRate=0.15, maxconf=None, useMaxConf="False")
+    g["sel_unc"], g["sel_X_L"] = unc, X_L
+    g["sel_X_L_next"], g["sel_X_U_next"] = xl, xu
+    np.random.seed(11)
+    xl2, xu2 = ns["update_X_L"](unc.copy(), X_all, X_L.copy(), 80)
+    g["sel2_X_L_next"], g["sel2_X_U_next"] = xl2, xu2
+    return g
+
+
+def main():
+    assert RL.available(), "reference tree not mounted"
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, spec_name, gids, pseed, sseed, sf, up2, clsw in CASES:
+        g = run_reference_case(spec_name, gids, pseed, sseed, sf, up2, clsw)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **g)
+        print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")
+    path = os.path.join(GOLDEN_DIR, "kats.npz")
+    np.savez_compressed(path, **kat_goldens())
+    print(path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

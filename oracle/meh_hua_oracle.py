@@ -188,18 +188,24 @@ def pre_stage(cls_scores: List[torch.Tensor], bbox_preds: List[torch.Tensor],
               L_scores: List[torch.Tensor], anchors: List[torch.Tensor], img_shapes, scale_factors,
               *, head: int, c_out: int, stds, nms_pre: int, score_thr: float, nms_iou: float,
               max_per_img: int, obj_thr: float = 0.3, cluster_iou: float = 0.5,
-              rescale: bool = True) -> Dict[str, object]:
+              rescale: bool = True, topk_override: Optional[List[torch.Tensor]] = None) -> Dict[str, object]:
+    """topk_override (stage isolation): per-level [B, K_s] prior indices to use instead
+    of this function's own topk result - lets a test feed a kernel's (near-tie re-ordered but
+    set-identical) row order into the later oracle stages."""
     B = cls_scores[0].shape[0]
-    lvl_scores, lvl_boxes, lvl_L, lvl_idx = [], [], [], []
-    for cls, reg, anc, lam in zip(cls_scores, bbox_preds, anchors, L_scores):
+    lvl_scores, lvl_boxes, lvl_L, lvl_idx, lvl_keys = [], [], [], [], []
+    for lv, (cls, reg, anc, lam) in enumerate(zip(cls_scores, bbox_preds, anchors, L_scores)):
         sc = score_rows(cls.float(), head, c_out)
         lm = lam.permute(0, 2, 3, 1).reshape(B, -1)
         dl = flatten_level(reg.float(), 4)
         an = anc[None].expand_as(dl)
         n = dl.shape[1]
         k = k_for_topk(nms_pre, n)
+        lvl_keys.append(topk_keys(sc, head))
         if k > 0:
             _, idx = topk_keys(sc, head).topk(k)
+            if topk_override is not None:
+                idx = topk_override[lv].long()
             bi = torch.arange(B).view(-1, 1).expand_as(idx)
             an, dl, sc, lm = an[bi, idx, :], dl[bi, idx, :], sc[bi, idx, :], lm[bi, idx]
         else:
@@ -224,7 +230,7 @@ def pre_stage(cls_scores: List[torch.Tensor], bbox_preds: List[torch.Tensor],
         keeps.append(cand[keep])                       # flat row*C + class index of each det
         objs = d[d[:, -1] > obj_thr][:, :4]            # GetObjectIdx, Lambda_L2.py:343-349
         pos.append(bbox_overlaps(boxes[j], objs) > cluster_iou)
-    return dict(lvl_scores=lvl_scores, lvl_L=lvl_L, lvl_idx=lvl_idx, boxes=boxes, scores=scores,
+    return dict(lvl_scores=lvl_scores, lvl_L=lvl_L, lvl_idx=lvl_idx, lvl_keys=lvl_keys, boxes=boxes, scores=scores,
                 dets=dets, labels=labels, det_flat=keeps, pos_bboxes=pos)
 
 
@@ -342,11 +348,12 @@ def score_batch(batch: Dict[str, object], *, head: int, c_out: int, stds, nms_pr
                 T: int = 500, fg_thr: float = 0.3, obj_thr: float = 0.3, cluster_iou: float = 0.5,
                 lambda_scale: float = 25.0, lambda_eps: float = 1e-7, use_lambda: bool = True,
                 agg: str = "objectSum_scaleMax_classSum", cls_w: bool = False,
-                sampler: SampleFn = default_sampler, rescale: bool = True) -> Dict[str, object]:
+                sampler: SampleFn = default_sampler, rescale: bool = True,
+                topk_override: Optional[List[torch.Tensor]] = None) -> Dict[str, object]:
     pre = pre_stage(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
                     batch["img_shapes"], batch["scale_factors"], head=head, c_out=c_out, stds=stds,
                     nms_pre=nms_pre, score_thr=score_thr, nms_iou=nms_iou, max_per_img=max_per_img,
-                    obj_thr=obj_thr, cluster_iou=cluster_iou, rescale=rescale)
+                    obj_thr=obj_thr, cluster_iou=cluster_iou, rescale=rescale, topk_override=topk_override)
     nested, flat, level_fg = compute_obj_unc(
         batch["cls_scores"], pre["pos_bboxes"], pre["lvl_scores"], pre["lvl_L"], head=head,
         c_out=c_out, T=T, fg_thr=fg_thr, lambda_scale=lambda_scale, lambda_eps=lambda_eps,

@@ -29,11 +29,34 @@ class Recorder:
         return smp
 
 
-def run_oracle(spec, batch, params: ScoringParams = None, seed: int = 1234):
+def run_oracle(spec, batch, params: ScoringParams = None, seed: int = 1234, topk_override=None):
     params = params or ScoringParams()
     rec = Recorder(seed)
-    out = O.score_batch(batch, sampler=rec, **O.spec_kwargs(spec, params))
+    out = O.score_batch(batch, sampler=rec, topk_override=topk_override, **O.spec_kwargs(spec, params))
     return out, rec
+
+
+def check_topk_order(spec, out, got_idx: np.ndarray, tie_tol: float = 2e-6):
+    """The kernel's per-level top-k against the oracle's: identical index SET per (image, level);
+    identical ORDER except where neighbouring keys are closer than tie_tol (relative) - torch's
+    softmax and the fused kernel round the last ulp differently, so such neighbours may swap.
+    Returns (override, n_swapped): per-level [B, K_s] index tensors in the kernel's order."""
+    koff = np.concatenate([[0], np.cumsum(spec.level_k)])
+    override, swapped = [], 0
+    for s in range(spec.num_levels):
+        want = out["lvl_idx"][s].numpy()
+        got = got_idx[:, koff[s]:koff[s + 1]].astype(np.int64)
+        assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1)), f"level {s}: top-k set differs"
+        if spec.level_sizes[s] > spec.level_k[s]:
+            keys = out["lvl_keys"][s].numpy()
+            for b in range(got.shape[0]):
+                k = keys[b][got[b]]
+                assert np.all(k[1:] <= k[:-1] * (1 + tie_tol)), f"level {s} image {b}: order beyond near-ties"
+                swapped += int((got[b] != want[b]).sum())
+        else:
+            assert np.array_equal(got, want)
+        override.append(torch.from_numpy(got))
+    return override, swapped
 
 
 def injection_buffers(spec, rec: Recorder, B: int, device):

@@ -7,7 +7,7 @@ import torch
 
 from aod_meh_hua_b200.scoring import Scorer
 from aod_meh_hua_b200.specs import HEAD_RETINA, ScoringParams
-from tests.helpers import injection_buffers, make_batch, oracle_pairs, run_oracle
+from tests.helpers import check_topk_order, injection_buffers, make_batch, oracle_pairs, run_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,12 @@ def _run(spec_name, gids, sf, params=None):
     B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
                 batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
     sc.k1()
+    torch.cuda.synchronize()
+    # stage isolation: near-tied neighbours in the top-k order may swap (last-ulp softmax rounding);
+    # the index set must be identical, and the later oracle stages then run in the kernel's row order
+    override, swapped = check_topk_order(spec, out, sc.result().topk_idx.cpu().numpy())
+    if swapped:
+        out, rec = run_oracle(spec, batch, params, topk_override=override)
     sc.nms()
     sc.pairs()
     inj, off = injection_buffers(spec, rec, B, sc.device)
@@ -51,8 +57,7 @@ def test_stagewise_parity(spec_name, gids, sf):
     for s in range(S):
         want = out["lvl_idx"][s].numpy()
         got = idx[:, koff[s]:koff[s + 1]]
-        assert np.array_equal(np.sort(got, axis=1), np.sort(want, axis=1)), f"level {s}: top-k set differs"
-        assert np.array_equal(got, want), f"level {s}: top-k order differs"
+        assert np.array_equal(got, want), f"level {s}: top-k rows differ from the (order-isolated) oracle"
     np.testing.assert_allclose(res.score_rows.cpu().numpy(), out["scores"].numpy(), rtol=RTOL, atol=1e-9)
     np.testing.assert_array_equal(res.lam_rows.cpu().numpy(), torch.cat(out["lvl_L"], dim=1).numpy())
     np.testing.assert_allclose(res.boxes.cpu().numpy(), out["boxes"].numpy(), rtol=RTOL, atol=1e-4)

@@ -1,0 +1,149 @@
+"""CPU: host-side logic - geometry tables, the C-ABI library's exports, loud failure without a
+GPU, pool sharding and the world_size-2 gather (gloo)."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from aod_meh_hua_b200 import _lib
+from aod_meh_hua_b200.pool import shard_range
+from aod_meh_hua_b200.specs import SPECS, ScoringParams, get_spec, parse_agg_spec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_survey_shape_table():
+    # N, K_tot and algorithmic bytes/image per BASELINE config
+    want = {
+        "cfg1_retina_r50_512_voc": (49104, 3720, 4.556e6),
+        "cfg2_ssd300_voc": (8732, 2790, 1.103e6),
+        "cfg3_retina_r50_800x1344_coco": (201600, 4693, 66.989e6),
+        "cfg3p_retina_r50_800x800_coco": (120087, 4441, 40.489e6),
+        "cfg4_ssd512_coco": (24564, 3500, 9.317e6),
+        "cfg5_retina_r101_1344_coco": (338454, 5000, 111.439e6),
+    }
+    for name, (n, k, nbytes) in want.items():
+        sp = get_spec(name)
+        assert sp.num_priors == n and sp.k_tot == k
+        assert abs(sp.k1_bytes_per_image() - nbytes) / nbytes < 1e-3
+
+
+def test_header_symbols_are_exported_and_bound():
+    """Every function include/mehhua.h declares is exported by libmehhua.so and bound in _lib."""
+    hdr = open(os.path.join(ROOT, "include", "mehhua.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mehhua_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mehhua_abi_version() == _lib.ABI_VERSION
+    assert lib.mehhua_launch_count() >= 0
+
+
+def test_struct_layouts_match_header():
+    lib = _lib.load()
+    # geometry-only entry points run without a GPU: rows per image and workspace size
+    from aod_meh_hua_b200.scoring import make_config
+    for name in ("cfg1_retina_r50_512_voc", "cfg2_ssd300_voc", "cfg3_retina_r50_800x1344_coco", "cfg4_ssd512_coco"):
+        sp = get_spec(name)
+        cfg = make_config(sp, ScoringParams(), 4096)
+        lv = _lib.LevelArray()
+        for s, ((h, w), a) in enumerate(zip(sp.featmaps, sp.num_anchors)):
+            lv[s].H, lv[s].W, lv[s].A = h, w, a
+        assert lib.mehhua_rows_per_image(C.byref(cfg), lv) == sp.k_tot
+        ws = lib.mehhua_workspace_bytes(C.byref(cfg), lv, 4)
+        num_fg = sp.num_classes
+        assert ws >= 4 * (4 * sp.num_priors + 8 * sp.k_tot * num_fg)
+    bad = make_config(get_spec("cfg2_ssd300_voc"), ScoringParams(), 4096)
+    bad.max_per_img = 10_000
+    assert lib.mehhua_workspace_bytes(C.byref(bad), lv, 4) == 0
+    assert b"max_per_img" in lib.mehhua_last_cuda_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from aod_meh_hua_b200.scoring import Scorer, pool_topk
+    with pytest.raises(_lib.MehhuaError):
+        Scorer(get_spec("tiny_retina_coco"))
+    with pytest.raises(_lib.MehhuaError):
+        pool_topk(torch.rand(10), 3)
+    lib = _lib.load()
+    out = (C.c_uint32 * 4)()
+    rc = lib.mehhua_debug_philox((C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0), out)
+    assert rc == _lib.E_NODEVICE
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "aod_meh_hua_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+            assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src, fn
+
+
+def test_shard_range_partitions_pool():
+    for n in (0, 1, 7, 100000, 1000003):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            for (a, b), (c, d) in zip(cuts[:-1], cuts[1:]):
+                assert b == c and 0 <= (b - a) - (d - c) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from aod_meh_hua_b200.pool import gather_scores, shard_range
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+for n in (11, 64, 1001):
+    full = torch.arange(n, dtype=torch.float32) * 0.5 + 1.0
+    a, b = shard_range(n, rank, world)
+    got = gather_scores(full[a:b].clone(), n, rank, world)
+    assert got.shape == (n,) and torch.equal(got, full), (rank, n)
+# world-size independence of the selected set: the top-k of the gathered scores is the same on
+# every rank and equals the single-process answer
+k = 7
+top = torch.topk(got, k).indices.sort().values
+ref = torch.topk(full, k).indices.sort().values
+assert torch.equal(top, ref)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_scores_world2_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT, port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
+
+
+def test_parse_agg_spec_tokens():
+    assert parse_agg_spec("objectSum_scaleMax_classSum") == (0, 2, 0)
+    assert parse_agg_spec("classAvg_objectMax_scaleSum") == (2, 0, 1)
+    with pytest.raises(KeyError):
+        parse_agg_spec("objectMin_scaleMax_classSum")
