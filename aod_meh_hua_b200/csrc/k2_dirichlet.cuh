@@ -4,13 +4,20 @@
 //   lambda' = mean(lambda_pairs) / (lambda + 1e-7) * 25;  alpha = score_row * lambda'
 //   x_t ~ Dirichlet(alpha), t = 1..T (T = 500)
 //   avg = mean_t x_t;  total = -sum_c avg ln avg;  ale = mean_t(-sum_c x ln x);  epi = total - ale
-// The sampler behind torch.distributions.Dirichlet is ATen's _sample_dirichlet (third party):
-// Marsaglia-Tsang gamma draws with the alpha<1 boost, normalised and clamped to
-// [FLT_MIN, 1 - 2^-24].  This kernel is written from the published algorithm (Marsaglia & Tsang
-// 2000), works in log space so tiny alphas do not underflow, draws its randomness from a
-// counter-based Philox4x32-10 keyed by (seed; image id, row, object, class, sample, attempt) and
-// never writes a sample to global memory: one warp owns a pair, lane = sample, the per-sample
-// log-gammas live in shared memory, class means are reduced with warp shuffles.
+// The sampler behind torch.distributions.Dirichlet is ATen's _sample_dirichlet (third party): gamma
+// draws normalised by their sum and clamped to [FLT_MIN, 1 - 2^-24].  This kernel is written from
+// the published algorithms and is exact in distribution, not bit-compatible with torch's stream:
+//   alpha >= 1 : Marsaglia & Tsang (2000) squeeze-free form, normal by Box-Muller
+//   alpha <  1 : Ahrens & Dieter (1974) algorithm GS - two uniforms, no normal, acceptance -> 1 as
+//                alpha -> 0, which is where almost every class of a softmax row lives
+// Everything is kept in LOG space (ln g), so alpha ~ 1e-5 draws (g ~ e^-100000) neither underflow
+// nor need special casing; the reference's FLT_MIN clamp only changes terms below 1e-36.
+// Randomness: counter-based Philox4x32-10 keyed by the seed, counter = (sample, call index, pair
+// identity (row, object), global image id) - independent of batch composition and world size.
+// Layout: one warp owns a pair; lane = sample (32 at a time).  ln g of the warp's 32 samples sits
+// in shared memory as lbuf[class][lane] (row stride 33: conflict-free both for the lane-private
+// accesses of the draw / normalise passes and for the transposed class-sum pass).  Samples never
+// touch global memory.
 #pragma once
 #include "common.cuh"
 
@@ -18,10 +25,9 @@ namespace mehhua {
 
 constexpr int kK2Threads = 256;
 constexpr int kK2Warps = kK2Threads / 32;
+constexpr int kLStride = 33;
 constexpr float kFltMin = 1.17549435e-38f;
-constexpr float kTopClamp = 0.99999994f;          // 1 - 2^-24
-constexpr float kLnFltMin = -87.33654475f;        // ln(FLT_MIN)
-constexpr float kLnTopClamp = -5.9604646e-08f;    // ln(1 - 2^-24)
+constexpr float kInvE = 0.36787944117144233f;
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -38,8 +44,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // uniform in (0,1) with 24-bit resolution, never 0 or 1
 __device__ __forceinline__ float u24(unsigned w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f; }
 
-// per-warp shared-memory carve-up (floats): lbuf[C*32] | alpha[C] | dd[C] | cc[C] | lnd[C] | inva[C] | avg[C]
-__host__ __device__ inline size_t k2_smem_bytes(int C) { return (size_t)kK2Warps * (C * 32 + 6 * C) * sizeof(float) + 1040 * sizeof(int); }
+// per-warp shared memory (floats): lbuf[C*33] | alpha,1/alpha [2C] | avg[C] | class lists [C bytes each x3]
+__host__ __device__ inline size_t k2_warp_floats(int C) {
+  const size_t f = (size_t)C * kLStride + (C & 1) + 3 * (size_t)C + (3 * (size_t)C + 3) / 4;
+  return (f + 3) & ~(size_t)3;
+}
+__host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_warp_floats(C) * sizeof(float) + 1040 * sizeof(int); }
 
 __global__ void __launch_bounds__(kK2Threads)
 k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ score_rows,
@@ -47,18 +57,18 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
                     const int* __restrict__ pair_row, const int* __restrict__ pair_obj,
                     const int* __restrict__ pair_off, const long long* __restrict__ image_ids,
                     const float* __restrict__ inj, const long long* __restrict__ inj_off,
-                    float* __restrict__ pair_unc, unsigned* __restrict__ status) {
+                    float* __restrict__ pair_unc, int* __restrict__ work_counter,
+                    unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k2_smem[];
   const int C = p.C, T = p.n_samples;
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
-  float* wbase = reinterpret_cast<float*>(img_pref + 1040) + (size_t)(threadIdx.x >> 5) * (C * 32 + 6 * C);
-  float* lbuf = wbase;
-  float* s_alpha = lbuf + C * 32;
-  float* s_dd = s_alpha + C;
-  float* s_cc = s_dd + C;
-  float* s_lnd = s_cc + C;
-  float* s_inva = s_lnd + C;
-  float* s_avg = s_inva + C;
+  float* wbase = reinterpret_cast<float*>(img_pref + 1040) + (size_t)(threadIdx.x >> 5) * k2_warp_floats(C);
+  float* lbuf = wbase;                                        // [C][33]
+  float2* s_cst = reinterpret_cast<float2*>(lbuf + C * kLStride + (C & 1));   // (alpha, 1/alpha), 8B aligned
+  float* s_avg = reinterpret_cast<float*>(s_cst + C);
+  unsigned char* s_small = reinterpret_cast<unsigned char*>(s_avg + C);
+  unsigned char* s_big = s_small + C;
+  unsigned char* s_bad = s_big + C;
 
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -69,11 +79,15 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   const int total = img_pref[p.B];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kK2Warps + (threadIdx.x >> 5);
-  const int nw = gridDim.x * kK2Warps;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const uint2 key = make_uint2((unsigned)(p.seed & 0xffffffffull), (unsigned)(p.seed >> 32));
+  const float fT = (float)T;
 
-  for (int g = gw; g < total; g += nw) {
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(work_counter, 1);
+    g = __shfl_sync(full, g, 0);
+    if (g >= total) break;
     // locate (image, pair) by binary search in the prefix
     int lo = 0, hi = p.B;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (img_pref[mid] <= g) lo = mid; else hi = mid; }
@@ -88,24 +102,33 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
     }
     const float* srow = score_rows + ((size_t)b * p.K + row) * C;
     __syncwarp();
-    for (int c = lane; c < C; c += 32) {
-      float a = __fmul_rn(srow[c], lamp);
-      if (!(a > 0.f) || !(a < 3.0e38f)) { a = 0.f; atomicOr(status, MEHHUA_ST_BAD_ALPHA); }
-      const float ash = a < 1.f ? a + 1.f : a;          // Marsaglia-Tsang shape (boosted when alpha < 1)
-      const float d = ash - (1.f / 3.f);
-      s_alpha[c] = a;
-      s_dd[c] = d;
-      s_cc[c] = rsqrtf(9.f * d);
-      s_lnd[c] = logf(d);
-      s_inva[c] = a > 0.f ? __fdiv_rn(1.f, a) : 0.f;
-      s_avg[c] = 0.f;
+    // class lists: big (alpha >= 1), small (0 < alpha < 1), bad (alpha <= 0, denormal-tiny or non-finite)
+    int nsmall = 0, nbig = 0, nbad = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      float a = 0.f;
+      if (c < C) a = __fmul_rn(srow[c], lamp);
+      const bool valid = c < C;
+      const bool bad = valid && (!(a > 1e-30f) || !(a < 3.0e38f));
+      const bool big = valid && !bad && a >= 1.f;
+      const bool small = valid && !bad && a < 1.f;
+      const unsigned mb = __ballot_sync(full, big), ms = __ballot_sync(full, small), mx = __ballot_sync(full, bad);
+      if (big) s_big[nbig + __popc(mb & lt_mask)] = (unsigned char)c;
+      if (small) s_small[nsmall + __popc(ms & lt_mask)] = (unsigned char)c;
+      if (bad) s_bad[nbad + __popc(mx & lt_mask)] = (unsigned char)c;
+      nbig += __popc(mb); nsmall += __popc(ms); nbad += __popc(mx);
+      if (valid) {
+        s_cst[c] = make_float2(bad ? 0.f : a, bad ? 0.f : __fdiv_rn(1.f, a));
+        s_avg[c] = 0.f;
+      }
     }
+    if (nbad > 0 && lane == 0) atomicOr(status, MEHHUA_ST_BAD_ALPHA);
     __syncwarp();
 
-    float ent_acc = 0.f;   // sum over this lane's samples of sum_c x ln x
+    float ent_acc = 0.f;   // sum over this lane's samples of (-sum_c x ln x)
     const long long ioff = (inj != nullptr && inj_off != nullptr) ? inj_off[b * p.S + s] : -1;
     if (ioff >= 0) {
-      // ---- injection mode: consume the oracle's drawn samples [T, P_bs, C] ----
+      // ---- injection mode: consume the oracle's drawn samples [T, P_bs, C]; reference formulas ----
       const int pb = pair_off[b * (p.S + 1) + s];
       const int P = pair_off[b * (p.S + 1) + s + 1] - pb;
       const int ql = q - pb;
@@ -115,7 +138,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         const float* xs = inj + ioff + ((size_t)(active ? t : 0) * P + ql) * C;
         for (int c = 0; c < C; ++c) {
           float x = active ? __ldg(xs + c) : 0.f;
-          if (active) ent_acc = __fmaf_rn(x, logf(x), ent_acc);
+          if (active) ent_acc = __fmaf_rn(-x, logf(x), ent_acc);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
           if (lane == 0) s_avg[c] += x;
@@ -128,68 +151,124 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
         const bool active = t < T;
-        int c = active ? 0 : C;
-        unsigned att = 0;
-        // flattened rejection loop: every iteration each unfinished lane makes one attempt for
-        // its current class, so lanes never idle while a neighbour retries
-        while (__any_sync(full, c < C)) {
-          if (c < C) {
-            const float a = s_alpha[c];
-            if (a <= 0.f) {
-              lbuf[c * 32 + lane] = -INFINITY;
-              ++c;
-            } else {
-              const uint4 w = philox4x32_10(make_uint4((unsigned)t, (unsigned)c | (att << 16), pid, gid), key);
-              const float r = sqrtf(-2.f * __logf(u24(w.x)));
+        float m = -INFINITY;
+        if (active) {
+          for (int i = 0; i < nbad; ++i) lbuf[s_bad[i] * kLStride + lane] = -INFINITY;
+          // Marsaglia-Tsang for the few classes with alpha >= 1
+          for (int i = 0; i < nbig; ++i) {
+            const int c = s_big[i];
+            const float d = s_cst[c].x - (1.f / 3.f);
+            const float cc = rsqrtf(9.f * d);
+            float l;
+            for (unsigned att = 0;; ++att) {
+              const uint4 w = philox4x32_10(make_uint4((unsigned)t, 0x80000000u | ((unsigned)c << 8) | (att & 255u), pid, gid), key);
+              const float r = sqrtf(-2.f * kLn2 * lg2_approx(u24(w.x)));
               const float x = r * __cosf((float)w.y * 1.4629180792671596e-09f);   // 2*pi / 2^32
-              const float v1 = fmaf(s_cc[c], x, 1.f);
-              bool ok = false;
-              float lv = 0.f;
+              const float v1 = fmaf(cc, x, 1.f);
               if (v1 > 0.f) {
-                lv = 3.f * __logf(v1);
+                const float lv = 3.f * kLn2 * lg2_approx(v1);
                 const float v = v1 * v1 * v1;
-                ok = __logf(u24(w.z)) < fmaf(s_dd[c], 1.f - v + lv, 0.5f * x * x);
+                if (kLn2 * lg2_approx(u24(w.z)) < fmaf(d, 1.f - v + lv, 0.5f * x * x)) { l = __logf(d) + lv; break; }
               }
-              if (ok) {
-                float l = s_lnd[c] + lv;
-                if (a < 1.f) l = fmaf(__logf(u24(w.w)), s_inva[c], l);
-                lbuf[c * 32 + lane] = l;
-                ++c;
-                att = 0;
-              } else {
-                ++att;
-              }
+            }
+            lbuf[c * kLStride + lane] = l;
+            m = fmaxf(m, l);
+          }
+        }
+        // Ahrens-Dieter GS for alpha < 1, flattened rejection loop: every iteration each unfinished
+        // lane makes one attempt for its current class, so lanes never idle while a neighbour retries
+        int i = active ? 0 : nsmall;
+        unsigned kcall = 0;
+        bool have = false;
+        uint2 spare = make_uint2(0u, 0u);
+        while (__any_sync(full, i < nsmall)) {
+          if (i < nsmall) {
+            unsigned r0, r1;
+            if (!have) {
+              const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key);
+              r0 = w.x; r1 = w.y; spare = make_uint2(w.z, w.w); have = true;
+            } else {
+              r0 = spare.x; r1 = spare.y; have = false;
+            }
+            const int c = s_small[i];
+            const float2 cs = s_cst[c];
+            const float bb = fmaf(cs.x, kInvE, 1.f);
+            const float pp = bb * u24(r0);
+            const float u2 = u24(r1);
+            float lnx;
+            bool ok;
+            if (pp <= 1.f) {          // x = pp^(1/alpha) in [0,1], accept with exp(-x)
+              const float l2 = lg2_approx(pp) * cs.y;          // log2 x
+              lnx = l2 * kLn2;
+              ok = u2 <= ex2_approx(-kLog2e * ex2_approx(l2));
+            } else {                  // x = -ln((b-p)/alpha) >= 1, accept with x^(alpha-1)
+              const float xx = -kLn2 * lg2_approx((bb - pp) * cs.y);
+              const float l2 = lg2_approx(xx);
+              lnx = l2 * kLn2;
+              ok = lg2_approx(u2) <= (cs.x - 1.f) * l2;
+            }
+            if (ok) {
+              lbuf[c * kLStride + lane] = lnx;
+              m = fmaxf(m, lnx);
+              ++i;
             }
           }
         }
         __syncwarp();
-        // normalise in log space: z = ln x = l - (max + ln sum exp(l - max))
-        float m = -INFINITY;
-        for (int cc = 0; cc < C; ++cc) m = fmaxf(m, lbuf[cc * 32 + lane]);
-        if (!(m > -INFINITY)) m = 0.f;
-        float A = 0.f;
-        for (int cc = 0; cc < C; ++cc) A += ex2_approx((lbuf[cc * 32 + lane] - m) * kLog2e);
-        const float zoff = m + __logf(A);
-        for (int cc = 0; cc < C; ++cc) {
-          const float z = lbuf[cc * 32 + lane] - zoff;
-          float x = ex2_approx(z * kLog2e);
-          x = fminf(fmaxf(x, kFltMin), kTopClamp);
-          const float zc = fminf(fmaxf(z, kLnFltMin), kLnTopClamp);
-          if (!active) x = 0.f;
-          else ent_acc = fmaf(x, zc, ent_acc);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
-          if (lane == 0) s_avg[cc] += x;
+        // normalise in log space.  e_c = exp(l_c - m); A = sum e = 1 + A' with the max term kept out
+        // of the sum (log1p keeps ln A accurate when one class owns the sample);
+        // -sum_c x ln x = ln A - (sum_c e_c d_c) / A with d_c = l_c - m
+        float inv_a = 0.f;
+        if (active) {
+          if (!(m > -INFINITY)) m = 0.f;
+          float ap = 0.f, bs = 0.f;
+          int nzero = 0;
+          for (int c = 0; c < C; ++c) {
+            const float d = fmaxf(lbuf[c * kLStride + lane] - m, -200.f);
+            const float e = ex2_approx(d * kLog2e);
+            if (d == 0.f) ++nzero; else ap += e;
+            bs = fmaf(e, d, bs);
+            lbuf[c * kLStride + lane] = e;
+          }
+          if (nzero > 0) {
+            ap += (float)(nzero - 1);
+            inv_a = __fdividef(1.f, 1.f + ap);
+            ent_acc += log1pf(ap) - bs * inv_a;
+          }
+        } else {
+          for (int c = 0; c < C; ++c) lbuf[c * kLStride + lane] = 0.f;
+        }
+        __syncwarp();
+        // class sums over the 32 samples, transposed: lane = class, walk the samples
+        for (int c0 = 0; c0 < C; c0 += 128) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const int c = c0 + lane;
+          const float* r0p = lbuf + (size_t)min(c, C - 1) * kLStride;
+          const float* r1p = lbuf + (size_t)min(c + 32, C - 1) * kLStride;
+          const float* r2p = lbuf + (size_t)min(c + 64, C - 1) * kLStride;
+          const float* r3p = lbuf + (size_t)min(c + 96, C - 1) * kLStride;
+          const int rem = C - c0;
+#pragma unroll 8
+          for (int tt = 0; tt < 32; ++tt) {
+            const float iv = __shfl_sync(full, inv_a, tt);
+            a0 = fmaf(r0p[tt], iv, a0);
+            if (rem > 32) a1 = fmaf(r1p[tt], iv, a1);
+            if (rem > 64) a2 = fmaf(r2p[tt], iv, a2);
+            if (rem > 96) a3 = fmaf(r3p[tt], iv, a3);
+          }
+          if (c < C) s_avg[c] += a0;
+          if (c + 32 < C) s_avg[c + 32] += a1;
+          if (c + 64 < C) s_avg[c + 64] += a2;
+          if (c + 96 < C) s_avg[c + 96] += a3;
         }
         __syncwarp();
       }
     }
     __syncwarp();
-    // epilogue: total = -sum_c avg ln avg, ale = -(1/T) sum_t sum_c x ln x
+    // epilogue: total = -sum_c avg ln avg, ale = (1/T) sum_t (-sum_c x ln x)
     float tot = 0.f;
-    const float fT = (float)T;
     for (int c = lane; c < C; c += 32) {
-      const float avg = __fdiv_rn(s_avg[c], fT);
+      const float avg = fmaxf(__fdiv_rn(s_avg[c], fT), kFltMin);
       tot = __fmaf_rn(-avg, logf(avg), tot);
     }
 #pragma unroll
@@ -198,7 +277,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       ent_acc += __shfl_xor_sync(full, ent_acc, o);
     }
     if (lane == 0) {
-      const float ale = -__fdiv_rn(ent_acc, fT);
+      const float ale = __fdiv_rn(ent_acc, fT);
       float* o3 = pair_unc + pq * 3;
       o3[0] = tot; o3[1] = ale; o3[2] = tot - ale;
     }

@@ -257,18 +257,22 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
   if (!o || !o->score_rows || !o->lam_rows || !o->lam_mean || !o->pair_row || !o->pair_obj || !o->pair_off ||
       !o->pair_unc)
     return arg_fail("null K2 buffer");
+  if (p.C > 256) return arg_fail("c_out must be <= 256 for the K2 class lists");
   const size_t smem = k2_smem_bytes(p.C);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K2 shared-memory layout");
   static size_t attr = 0;
-  if (smem > attr) {
+  static int blocks_per_sm = 1;
+  if (smem != attr) {
     CU(cudaFuncSetAttribute(k2_dirichlet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k2_dirichlet_kernel, kK2Threads, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     attr = smem;
   }
-  const int per_sm = (int)((227 * 1024) / smem) > 2 ? 2 : ((227 * 1024) / smem >= 1 ? (int)((227 * 1024) / smem) : 1);
-  k2_dirichlet_kernel<<<sm_count() * per_sm, kK2Threads, smem, st>>>(
+  CU(cudaMemsetAsync(ws.work_counter, 0, sizeof(int), st));
+  k2_dirichlet_kernel<<<sm_count() * blocks_per_sm, kK2Threads, smem, st>>>(
       p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off,
       reinterpret_cast<const long long*>(image_ids), inj, reinterpret_cast<const long long*>(inj_off),
-      o->pair_unc, ws.status);
+      o->pair_unc, ws.work_counter, ws.status);
   LAUNCHED("k2_dirichlet_kernel");
   return 0;
 }

@@ -1,0 +1,234 @@
+"""Drop-in boundary: the reference's head / API methods for the scoring path, backed by the CUDA
+kernels.  Same names, argument meaning and return types as the reference so that
+tools/train_RetinaNet.py / tools/train_SSD.py keep working unchanged:
+
+  B200ScoringMixin._get_bboxes          <- Lambda_L2Net._get_bboxes   (Lambda_L2.py:254-384)
+                                           MyLSSDHead._get_bboxes     (My_L_ssd_head.py:315-433)
+  B200ScoringMixin.ComputeObjUnc        <- Lambda_L2.py:489-537 / My_L_ssd_head.py:435-482
+  B200ScoringMixin.AggregateObjScaleUnc <- Lambda_L2.py:597-619 / My_L_ssd_head.py:517-539
+  calculate_uncertainty                 <- mmdet/apis/test.py:65-70, 90-135
+  update_X_L                            <- mmdet/utils/active_datasets.py:102-135 (pool.py)
+
+The mixin goes in front of the reference head in the MRO (`class Lambda_L2Net_B200(
+B200ScoringMixin, Lambda_L2Net)`, see register_heads / INTEGRATION.md).  Only the Entropy_NMS
+scoring route is taken over; every other route (evaluation with isEval=True, Entropy_ALL,
+ONNX export) falls through to the reference method via super().
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .pool import update_X_L  # noqa: F401  (re-exported: same signature as the reference's)
+from .scoring import Scorer
+from .specs import HEAD_RETINA, HEAD_SSD, DetectorSpec, ScoringParams, parse_agg_spec
+
+
+def _spec_from_head(head, featmaps: Sequence[Tuple[int, int]], num_anchors: Sequence[int], img_hw) -> DetectorSpec:
+    act = getattr(head, "last_activation", "relu")
+    kind = HEAD_SSD if act == "softmax" else HEAD_RETINA
+    c_out = int(head.cls_out_channels)
+    cfg = head.test_cfg
+    stds = tuple(float(v) for v in getattr(head.bbox_coder, "stds", (1.0, 1.0, 1.0, 1.0)))
+    means = tuple(float(v) for v in getattr(head.bbox_coder, "means", (0.0, 0.0, 0.0, 0.0)))
+    if any(m != 0.0 for m in means):
+        raise NotImplementedError("non-zero bbox_coder target_means")
+    nms = cfg["nms"] if isinstance(cfg, dict) else cfg.nms
+    return DetectorSpec(
+        name=f"head_{kind}_{c_out}_{tuple(featmaps)}", head=kind,
+        num_classes=c_out - (1 if kind == HEAD_SSD else 0), img_hw=tuple(img_hw),
+        strides=tuple(range(len(featmaps))), featmaps=tuple(tuple(f) for f in featmaps),
+        num_anchors=tuple(num_anchors), target_stds=stds, score_thr=float(cfg.get("score_thr")),
+        max_per_img=int(cfg.get("max_per_img")), nms_pre=int(cfg.get("nms_pre", -1)),
+        nms_iou=float(nms.get("iou_threshold", 0.5)))
+
+
+class B200ScoringMixin:
+    """Put in front of Lambda_L2Net / MyLSSDHead.  Head attributes used: cls_out_channels,
+    last_activation, test_cfg, bbox_coder.{means,stds} - exactly what the reference method reads."""
+
+    mehhua_params = ScoringParams()     # reference constants; override per class / instance for ablations
+    mehhua_max_batch = 8
+    _mehhua_scorers: Dict[tuple, Scorer]
+
+    def _mehhua_scorer(self, cls_scores: List[torch.Tensor], img_hw, uPool2: str, clsW: bool) -> Scorer:
+        B = cls_scores[0].shape[0]
+        featmaps = [tuple(c.shape[-2:]) for c in cls_scores]
+        c_out = int(self.cls_out_channels)
+        num_anchors = [c.shape[1] // c_out for c in cls_scores]
+        device = cls_scores[0].device
+        key = (tuple(featmaps), tuple(num_anchors), c_out, str(device), uPool2, bool(clsW),
+               max(B, self.mehhua_max_batch))
+        cache = self.__dict__.setdefault("_mehhua_scorers", {})
+        if key not in cache:
+            spec = _spec_from_head(self, featmaps, num_anchors, img_hw)
+            p = self.mehhua_params
+            params = ScoringParams(n_samples=p.n_samples, fg_thr=p.fg_thr, obj_thr=p.obj_thr,
+                                   cluster_iou=p.cluster_iou, lambda_scale=p.lambda_scale,
+                                   lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, agg=uPool2,
+                                   cls_w=bool(clsW), seed=p.seed)
+            parse_agg_spec(uPool2)       # KeyError for specs without object/scale/class, as the reference
+            cache[key] = Scorer(spec, params, max_batch=max(B, self.mehhua_max_batch), device=device)
+        return cache[key]
+
+    # ------------------------------------------------------------------ widest boundary
+    def _get_bboxes(self, mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors, cfg,
+                    rescale=False, with_nms=True, **kwargs):
+        scoring = bool(kwargs.get("isUnc")) and kwargs.get("uPool") == "Entropy_NMS" and with_nms \
+            and "L_scores" in kwargs and not torch.onnx.is_in_onnx_export()
+        if not scoring or (cfg is not None and cfg is not self.test_cfg):
+            return super()._get_bboxes(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors,
+                                       cfg, rescale, with_nms, **kwargs)
+        if kwargs.get("scaleUnc"):
+            raise NotImplementedError("scaleUnc=True is undefined on the Entropy_NMS route of the reference")
+        B = mlvl_cls_scores[0].shape[0]
+        hw = tuple(int(v) for v in img_shapes[0][:2])
+        sc = self._mehhua_scorer(list(mlvl_cls_scores), hw, kwargs["uPool2"], kwargs.get("clsW", False))
+        if bool(sc.cfg.rescale) != bool(rescale):
+            sc.cfg.rescale = int(bool(rescale))
+        ids = kwargs.get("image_ids")
+        if ids is None and "batchIdx" in kwargs:
+            ids = [int(kwargs["batchIdx"]) * B + j for j in range(B)]    # apis/test.py:115 batchIdx=i
+        res = sc.score(mlvl_cls_scores, mlvl_bbox_preds, kwargs["L_scores"], mlvl_anchors, img_shapes,
+                       scale_factors, image_ids=ids)
+        n_det = res.n_det.cpu().tolist()
+        det_results = [(res.dets[b, :n_det[b]].clone(), res.det_labels[b, :n_det[b]].long())
+                       for b in range(B)]
+        agged = [float(v) if v != 0 else 0 for v in res.image_scores.cpu().tolist()]
+        if kwargs.get("saveMaxConf"):
+            maxconf = max_conf(mlvl_cls_scores, int(self.cls_out_channels))[0]
+            return det_results, agged, maxconf
+        return det_results, agged
+
+    # ------------------------------------------------------------------ narrowest boundary
+    def ComputeObjUnc(self, mlvl_cls_scores, pos_bboxes, mlvl_scores, mlvl_Ls, mlvl_idces):
+        """Same inputs / nested output as the reference: output[i][obj][s][str(cls)] = (ale, epi)
+        0-d tensors.  Cluster masks and kept rows come from the caller (as in the reference); the
+        Dirichlet sampling runs in K2."""
+        S = len(mlvl_cls_scores)
+        B = mlvl_cls_scores[0].shape[0]
+        dev = mlvl_scores[0].device
+        c_out = int(self.cls_out_channels)
+        p = self.mehhua_params
+        ssd = getattr(self, "last_activation", "relu") == "softmax"
+        out = [[[{} for _ in range(S)] for _ in range(pos_bboxes[b].size(1))] for b in range(B)]
+        ksz = [m.shape[1] for m in mlvl_scores]
+        koff = np.concatenate([[0], np.cumsum(ksz)])
+        rows_t = torch.cat(list(mlvl_scores), dim=1).float().contiguous()
+        lam_t = torch.cat(list(mlvl_Ls), dim=1).float().contiguous()
+        from .scoring import pair_uncertainty
+        for s in range(S):
+            x = mlvl_cls_scores[s]
+            x = x.permute(0, 2, 3, 1).reshape(B, -1, c_out)
+            conf = x.softmax(dim=2)
+            conf = conf[..., :-1].max(dim=2)[0] if ssd else conf.max(dim=2)[0]
+            level_fg = (conf > p.fg_thr).any(dim=1).cpu().tolist()
+            for i in range(B):
+                if not level_fg[i]:
+                    continue
+                rows = mlvl_scores[s][i]
+                fgpos = pos_bboxes[i][koff[s]:koff[s + 1]] & (rows.max(dim=1)[0] > p.fg_thr)[:, None]
+                nz = fgpos.nonzero()
+                if nz.shape[0] == 0:
+                    continue
+                pidx, oidx = nz[:, 0], nz[:, 1]
+                unc = pair_uncertainty(rows_t[i], lam_t[i], pidx + int(koff[s]), oidx, p, seed_ids=(i, s))
+                pcls = rows[pidx].argmax(dim=1)
+                for obj in oidx.unique():
+                    om = oidx == obj
+                    for c in pcls[om].unique():
+                        m = om & (pcls == c)
+                        out[i][obj][s][f"{c}"] = (unc[m, 1].mean(), unc[m, 2].mean())
+        return out
+
+    def AggregateObjScaleUnc(self, objScaleClsUnc, type, clsW=False, **kwargs):
+        """Nested-dict input -> list of python floats (0 for images without objects).  The input is
+        a host-side Python structure, so this compatibility method reduces it on the host; the fused
+        route (_get_bboxes) aggregates on the GPU in K3c."""
+        ops = parse_agg_spec(type)
+        red = {0: lambda v: float(np.float32(np.sum(np.asarray(v, dtype=np.float32)))),
+               1: lambda v: float(np.float32(np.mean(np.asarray(v, dtype=np.float32)))),
+               2: lambda v: float(np.float32(np.max(np.asarray(v, dtype=np.float32))))}
+        f_obj, f_scale, f_cls = red[ops[0]], red[ops[1]], red[ops[2]]
+        output = []
+        for img in objScaleClsUnc:
+            per_obj, seen = [], set()
+            for obj in img:
+                per_lvl = []
+                for lvl in obj:
+                    vals = [float(epi) for (_, epi) in lvl.values()]
+                    seen.update(lvl.keys())
+                    if vals:
+                        per_lvl.append(f_cls(vals))
+                if per_lvl:
+                    per_obj.append(f_scale(per_lvl))
+            output.append(f_obj(per_obj) if per_obj else 0)
+            if clsW:
+                output[-1] *= len(seen)
+        return output
+
+
+def max_conf(mlvl_cls_scores, n_cls: int):
+    """getMaxConf (mmdet/utils/functions.py:467-476): per image max softmax probability over all
+    levels (only used when saveMaxConf=True; not on the hot path)."""
+    B = mlvl_cls_scores[0].size(0)
+    out = torch.zeros(B, len(mlvl_cls_scores), device=mlvl_cls_scores[0].device)
+    for s, cs in enumerate(mlvl_cls_scores):
+        x = cs.permute(0, 2, 3, 1).reshape(B, -1, n_cls)
+        out[:, s] = x.softmax(dim=-1).reshape(B, -1).max(dim=-1)[0]
+    return out.max(dim=-1)[0].tolist(), out
+
+
+def calculate_uncertainty(cfg, model, data_loader, **kwargs):
+    """Mirror of calculate_uncertainty -> Uncertainty_fns.Entropy_NMS -> single_gpu_uncertainty
+    (apis/test.py:52-70, 90-135): loops the pool loader in order and returns the list of 0-d CPU
+    tensors the AL scripts stack (tools/train_RetinaNet.py:242-245).  Unlike the reference it does
+    not swallow a failing batch (apis/test.py:122-128 would silently misalign image indices)."""
+    if cfg.uncertainty_pool != "Entropy_NMS":
+        raise NotImplementedError(f"uncertainty_pool={cfg.uncertainty_pool!r}: only Entropy_NMS is taken over")
+    if "scaleUnc" not in kwargs:
+        raise KeyError("scaleUnc")          # the reference reads kwargs['scaleUnc'] unconditionally (:129)
+    model.eval()
+    uncertainties, maxconfs = [], []
+    with torch.no_grad():
+        for i, data in enumerate(data_loader):
+            data = dict(data)
+            data["img"] = getattr(data["img"], "data", data["img"])
+            data["img_metas"] = getattr(data["img_metas"], "data", data["img_metas"])
+            result, *unc = model(return_loss=False, rescale=True, isEval=False, batchIdx=i, isUnc=cfg.uncertainty_type,
+                                 uPool=cfg.uncertainty_pool, uPool2=cfg.uncertainty_pool2, **data, **kwargs)
+            others = unc[1:]
+            unc = unc[0]
+            while isinstance(unc[0], list):
+                unc = unc[0]
+            if len(unc) != len(result):
+                raise _lib.MehhuaError(f"batch {i}: {len(unc)} scores for {len(result)} images")
+            uncertainties.extend(unc)
+            if kwargs.get("saveMaxConf"):
+                maxconfs.extend(others[0])
+    out = torch.tensor(uncertainties)
+    if kwargs.get("saveMaxConf"):
+        return [out, maxconfs]
+    return [x.cpu() for x in out]
+
+
+def register_heads():
+    """Register `Lambda_L2Net_B200` / `MyLSSDHead_B200` with the reference's HEADS registry (needs
+    the reference's mmdet + mmcv importable).  Select with `--bbox-head Lambda_L2Net_B200`
+    (tools/train_RetinaNet.py:59,90) or `bbox_head=dict(type='Lambda_L2Net_B200', ...)`."""
+    from mmdet.models.builder import HEADS
+    from mmdet.models.dense_heads.Lambda_L2 import Lambda_L2Net
+    from mmdet.models.dense_heads.My_L_ssd_head import MyLSSDHead
+
+    @HEADS.register_module()
+    class Lambda_L2Net_B200(B200ScoringMixin, Lambda_L2Net):
+        pass
+
+    @HEADS.register_module()
+    class MyLSSDHead_B200(B200ScoringMixin, MyLSSDHead):
+        pass
+
+    return Lambda_L2Net_B200, MyLSSDHead_B200

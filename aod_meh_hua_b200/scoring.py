@@ -272,3 +272,52 @@ def pool_topk(scores: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None)
     _lib.check(lib.mehhua_k4_pool_topk(scores.data_ptr(), mp, n, k, out.data_ptr(), nsel.data_ptr(),
                                        ws.data_ptr(), 256, st), "mehhua_k4_pool_topk")
     return out[: int(nsel.item())]
+
+
+def pair_uncertainty(rows: torch.Tensor, lam: torch.Tensor, pair_row: torch.Tensor, pair_obj: torch.Tensor,
+                     params: ScoringParams, seed_ids=(0, 0), inj_samples: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K2 on an explicit pair list of ONE (image, level): rows [K, C] scores, lam [K], pair_row /
+    pair_obj [P] -> [P, 3] (total, aleatoric, epistemic).  Used by the ComputeObjUnc compatibility
+    method, whose cluster masks come from the caller.  lambda' = mean(lam[pair_row]) / (lam + eps)
+    * scale as in Lambda_L2.py:513-515."""
+    lib = _lib.load()
+    if not rows.is_cuda:
+        raise _lib.MehhuaError("pair_uncertainty needs CUDA tensors; there is no CPU fallback")
+    dev = rows.device
+    K, Cc = int(rows.shape[0]), int(rows.shape[1])
+    P = int(pair_row.numel())
+    cfg = _lib.Config()
+    cfg.head, cfg.c_out, cfg.num_levels, cfg.nms_pre = 0, Cc, 1, -1
+    cfg.score_thr, cfg.nms_iou, cfg.max_per_img = 0.05, 0.5, 1
+    cfg.fg_thr, cfg.obj_thr, cfg.cluster_iou = params.fg_thr, params.obj_thr, params.cluster_iou
+    cfg.lambda_scale, cfg.lambda_eps, cfg.use_lambda = params.lambda_scale, params.lambda_eps, int(params.use_lambda)
+    cfg.n_samples = params.n_samples
+    cfg.agg_object = cfg.agg_scale = cfg.agg_class = 0
+    cfg.stds = (C.c_float * 4)(1, 1, 1, 1)
+    cfg.wh_ratio_clip, cfg.rescale, cfg.pair_cap, cfg.seed = 16 / 1000, 0, max(P, 1), params.seed
+    lv = _lib.LevelArray()
+    lv[0].H, lv[0].W, lv[0].A = 1, K, 1
+    rows = rows.float().contiguous()
+    lam = lam.float().contiguous()
+    prow = pair_row.to(device=dev, dtype=torch.int32).contiguous()
+    pobj = pair_obj.to(device=dev, dtype=torch.int32).contiguous()
+    poff = torch.tensor([0, P], dtype=torch.int32, device=dev)
+    lmean = lam[pair_row.long()].mean().reshape(1).float() if P else torch.zeros(1, device=dev)
+    unc = torch.zeros(max(P, 1), 3, device=dev)
+    bufs = _lib.Buffers()
+    bufs.score_rows, bufs.lam_rows, bufs.lam_mean = rows.data_ptr(), lam.data_ptr(), lmean.data_ptr()
+    bufs.pair_row, bufs.pair_obj, bufs.pair_off, bufs.pair_unc = prow.data_ptr(), pobj.data_ptr(), poff.data_ptr(), unc.data_ptr()
+    ws_bytes = int(lib.mehhua_workspace_bytes(C.byref(cfg), lv, 1))
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    ids = torch.tensor([int(seed_ids[0]) * 64 + int(seed_ids[1])], dtype=torch.int64, device=dev)
+    ip = io = None
+    keep = None
+    if inj_samples is not None:
+        keep = (inj_samples.to(dev).float().contiguous(), torch.zeros(1, dtype=torch.int64, device=dev))
+        ip, io = keep[0].data_ptr(), keep[1].data_ptr()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    if P:
+        _lib.check(lib.mehhua_k2_dirichlet_epi(C.byref(cfg), lv, 1, ids.data_ptr(), ip, io, C.byref(bufs),
+                                               ws.data_ptr(), ws_bytes, st), "mehhua_k2_dirichlet_epi")
+        torch.cuda.current_stream(dev).synchronize()
+    return unc[:P]

@@ -170,3 +170,34 @@ def test_pool_topk_matches_stable_argsort():
     few[[3, 77, 9000]] = True
     got = pool_topk(scores.cuda(), 10, few.cuda()).cpu().numpy()
     assert sorted(got.tolist()) == [3, 77, 9000]
+
+
+def test_sampler_moments_across_alpha_regimes():
+    """K2's gamma samplers (Ahrens-Dieter GS for alpha < 1, Marsaglia-Tsang for alpha >= 1) against
+    the Dirichlet closed forms, on hand-picked alpha rows that straddle the algorithm boundary and
+    reach the tiny-alpha regime of softmax rows.  T = 200k samples -> MC error ~1e-3."""
+    from aod_meh_hua_b200.scoring import pair_uncertainty
+    from oracle import meh_hua_oracle as O
+    rows = [
+        [0.5, 0.5, 0.5, 0.5, 0.5, 0.5],
+        [5.0, 0.01, 0.001, 2.0, 0.3, 0.7],
+        [0.9, 0.95, 0.999, 1.0, 1.001, 1.05],
+        [1e-4, 1e-3, 30.0, 1e-5, 1e-2, 1e-6],
+        [0.3, 0.3, 0.3, 0.3, 0.3, 0.3],
+        [12.0, 7.0, 3.0, 1.5, 1.0, 25.0],
+        [0.05, 0.02, 0.08, 0.6, 0.11, 0.04],
+    ]
+    alpha = torch.tensor(rows, dtype=torch.float32, device="cuda:0")
+    P = alpha.shape[0]
+    params = ScoringParams(n_samples=200_000, use_lambda=False)
+    unc = pair_uncertainty(alpha, torch.ones(P, device="cuda:0"), torch.arange(P), torch.zeros(P, dtype=torch.long),
+                           params, seed_ids=(3, 1)).cpu().numpy().astype(np.float64)
+    h, e_ent, epi = O.dirichlet_expectations(np.asarray(rows, dtype=np.float64))
+    np.testing.assert_allclose(unc[:, 0], h, rtol=5e-3, atol=2e-3)        # total = H(mean_t x)
+    np.testing.assert_allclose(unc[:, 1], e_ent, rtol=5e-3, atol=2e-3)    # aleatoric = E[H(x)]
+    np.testing.assert_allclose(unc[:, 2], epi, rtol=2e-2, atol=3e-3)
+    # a second seed gives a different stream but the same moments
+    unc2 = pair_uncertainty(alpha, torch.ones(P, device="cuda:0"), torch.arange(P), torch.zeros(P, dtype=torch.long),
+                            params, seed_ids=(4, 1)).cpu().numpy().astype(np.float64)
+    assert not np.array_equal(unc, unc2)
+    np.testing.assert_allclose(unc2[:, 1], e_ent, rtol=5e-3, atol=2e-3)
