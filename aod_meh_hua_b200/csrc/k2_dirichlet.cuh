@@ -28,6 +28,7 @@ constexpr int kK2Warps = kK2Threads / 32;
 constexpr int kLStride = 33;
 constexpr float kFltMin = 1.17549435e-38f;
 constexpr float kInvE = 0.36787944117144233f;
+constexpr float kTwoM32 = 2.3283064365386963e-10f;   // 2^-32
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -44,12 +45,52 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // uniform in (0,1) with 24-bit resolution, never 0 or 1
 __device__ __forceinline__ float u24(unsigned w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f; }
 
-// per-warp shared memory (floats): lbuf[C*33] | alpha,1/alpha [2C] | avg[C] | class lists [C bytes each x3]
+// shared-memory accessors on 32-bit shared-window addresses (keeps address arithmetic in one IMAD)
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
+__device__ __forceinline__ float4 lds_v4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+// per-warp shared memory, in floats:
+//   cst4[C] (float4: b*2^-32, 1/alpha, alpha-1, b) | lbuf[C*33] | alpha[C] | avg[C] | lists 3 x C bytes
 __host__ __device__ inline size_t k2_warp_floats(int C) {
-  const size_t f = (size_t)C * kLStride + (C & 1) + 3 * (size_t)C + (3 * (size_t)C + 3) / 4;
+  const size_t f = 4 * (size_t)C + (size_t)C * kLStride + 2 * (size_t)C + (3 * (size_t)C + 3) / 4;
   return (f + 3) & ~(size_t)3;
 }
 __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_warp_floats(C) * sizeof(float) + 1040 * sizeof(int); }
+
+// One Ahrens-Dieter GS attempt for the class at position i of the small-alpha list, branch-free.
+// Works in log2 units: on acceptance stores l2 = log2(gamma draw) and advances the cursor by 2.
+//   p = b*U1;  p <= 1: x = p^(1/alpha), accept iff U2 <= exp(-x)
+//              p >  1: x = -ln((b-p)/alpha) >= 1, accept iff U2 <= x^(alpha-1)
+// both tests are done as log2(U2) <= rhs.
+__device__ __forceinline__ void gs_attempt(int& i, const int nsmall, const unsigned w0, const unsigned w1,
+                                           const unsigned s_small, const unsigned s_cst4, const unsigned lrow,
+                                           float& m) {
+  if (i < nsmall) {
+    const unsigned c = lds_u8(s_small + i);
+    const float4 k = lds_v4(s_cst4 + c * 16u);            // b*2^-32, 1/alpha, alpha-1, b
+    const float pp = (float)w0 * k.x;
+    const bool lo = pp <= 1.f;
+    const float q = lo ? pp : (k.w - pp) * k.y;
+    const float lq = lg2_approx(q);
+    const float l2a = lq * k.y;                           // log2 x, first branch
+    const float rhsa = -kLog2e * ex2_approx(l2a);         // log2 exp(-x)
+    const float l2b = lg2_approx(-kLn2 * lq);             // log2 x, second branch
+    const float rhsb = k.z * l2b;                         // log2 x^(alpha-1)
+    const float l2 = lo ? l2a : l2b;
+    const float rhs = lo ? rhsa : rhsb;
+    if (lg2_approx((float)w1) - 32.f <= rhs) {
+      sts_f32(lrow + c * (kLStride * 4u), l2);
+      m = fmaxf(m, l2);
+      i += 2;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kK2Threads)
 k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ score_rows,
@@ -63,12 +104,17 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   const int C = p.C, T = p.n_samples;
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
   float* wbase = reinterpret_cast<float*>(img_pref + 1040) + (size_t)(threadIdx.x >> 5) * k2_warp_floats(C);
-  float* lbuf = wbase;                                        // [C][33]
-  float2* s_cst = reinterpret_cast<float2*>(lbuf + C * kLStride + (C & 1));   // (alpha, 1/alpha), 8B aligned
-  float* s_avg = reinterpret_cast<float*>(s_cst + C);
+  float4* cst4 = reinterpret_cast<float4*>(wbase);            // [C]
+  float* lbuf = wbase + 4 * C;                                // [C][33], log2 units
+  float* s_alpha = lbuf + C * kLStride;                       // [C]
+  float* s_avg = s_alpha + C;                                 // [C]
   unsigned char* s_small = reinterpret_cast<unsigned char*>(s_avg + C);
   unsigned char* s_big = s_small + C;
   unsigned char* s_bad = s_big + C;
+  const int lane = threadIdx.x & 31;
+  const unsigned a_cst4 = (unsigned)__cvta_generic_to_shared(cst4);
+  const unsigned a_small = (unsigned)__cvta_generic_to_shared(s_small);
+  const unsigned a_lrow = (unsigned)__cvta_generic_to_shared(lbuf) + 4u * lane;   // my column of row 0
 
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -78,7 +124,6 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   __syncthreads();
   const int total = img_pref[p.B];
   const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const uint2 key = make_uint2((unsigned)(p.seed & 0xffffffffull), (unsigned)(p.seed >> 32));
   const float fT = (float)T;
@@ -118,7 +163,9 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       if (bad) s_bad[nbad + __popc(mx & lt_mask)] = (unsigned char)c;
       nbig += __popc(mb); nsmall += __popc(ms); nbad += __popc(mx);
       if (valid) {
-        s_cst[c] = make_float2(bad ? 0.f : a, bad ? 0.f : __fdiv_rn(1.f, a));
+        const float bb = fmaf(a, kInvE, 1.f);
+        cst4[c] = make_float4(bb * kTwoM32, bad ? 0.f : __fdiv_rn(1.f, a), a - 1.f, bb);
+        s_alpha[c] = bad ? 0.f : a;
         s_avg[c] = 0.f;
       }
     }
@@ -145,7 +192,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         }
       }
     } else {
-      // ---- free-running sampler ----
+      // ---- free-running sampler (log2 units throughout) ----
       const unsigned gid = image_ids ? (unsigned)image_ids[b] : (unsigned)b;
       const unsigned pid = (unsigned)row | ((unsigned)obj << 20);
       for (int t0 = 0; t0 < T; t0 += 32) {
@@ -157,86 +204,61 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
           // Marsaglia-Tsang for the few classes with alpha >= 1
           for (int i = 0; i < nbig; ++i) {
             const int c = s_big[i];
-            const float d = s_cst[c].x - (1.f / 3.f);
+            const float d = s_alpha[c] - (1.f / 3.f);
             const float cc = rsqrtf(9.f * d);
-            float l;
+            float l2;
             for (unsigned att = 0;; ++att) {
               const uint4 w = philox4x32_10(make_uint4((unsigned)t, 0x80000000u | ((unsigned)c << 8) | (att & 255u), pid, gid), key);
               const float r = sqrtf(-2.f * kLn2 * lg2_approx(u24(w.x)));
               const float x = r * __cosf((float)w.y * 1.4629180792671596e-09f);   // 2*pi / 2^32
               const float v1 = fmaf(cc, x, 1.f);
               if (v1 > 0.f) {
-                const float lv = 3.f * kLn2 * lg2_approx(v1);
+                const float lv2 = 3.f * lg2_approx(v1);
                 const float v = v1 * v1 * v1;
-                if (kLn2 * lg2_approx(u24(w.z)) < fmaf(d, 1.f - v + lv, 0.5f * x * x)) { l = __logf(d) + lv; break; }
+                if (kLn2 * lg2_approx(u24(w.z)) < fmaf(d, fmaf(kLn2, lv2, 1.f - v), 0.5f * x * x)) { l2 = lg2_approx(d) + lv2; break; }
               }
             }
-            lbuf[c * kLStride + lane] = l;
-            m = fmaxf(m, l);
+            lbuf[c * kLStride + lane] = l2;
+            m = fmaxf(m, l2);
           }
         }
-        // Ahrens-Dieter GS for alpha < 1, flattened rejection loop: every iteration each unfinished
-        // lane makes one attempt for its current class, so lanes never idle while a neighbour retries
-        int i = active ? 0 : nsmall;
+        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with two cursors (even / odd
+        // list positions): each iteration one Philox block feeds one attempt per cursor, so a lane
+        // never idles while a neighbour retries and the two attempts overlap in the pipelines.
+        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall;
         unsigned kcall = 0;
-        bool have = false;
-        uint2 spare = make_uint2(0u, 0u);
-        while (__any_sync(full, i < nsmall)) {
-          if (i < nsmall) {
-            unsigned r0, r1;
-            if (!have) {
-              const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key);
-              r0 = w.x; r1 = w.y; spare = make_uint2(w.z, w.w); have = true;
-            } else {
-              r0 = spare.x; r1 = spare.y; have = false;
-            }
-            const int c = s_small[i];
-            const float2 cs = s_cst[c];
-            const float bb = fmaf(cs.x, kInvE, 1.f);
-            const float pp = bb * u24(r0);
-            const float u2 = u24(r1);
-            float lnx;
-            bool ok;
-            if (pp <= 1.f) {          // x = pp^(1/alpha) in [0,1], accept with exp(-x)
-              const float l2 = lg2_approx(pp) * cs.y;          // log2 x
-              lnx = l2 * kLn2;
-              ok = u2 <= ex2_approx(-kLog2e * ex2_approx(l2));
-            } else {                  // x = -ln((b-p)/alpha) >= 1, accept with x^(alpha-1)
-              const float xx = -kLn2 * lg2_approx((bb - pp) * cs.y);
-              const float l2 = lg2_approx(xx);
-              lnx = l2 * kLn2;
-              ok = lg2_approx(u2) <= (cs.x - 1.f) * l2;
-            }
-            if (ok) {
-              lbuf[c * kLStride + lane] = lnx;
-              m = fmaxf(m, lnx);
-              ++i;
-            }
+        while (__any_sync(full, (ia < nsmall) | (ib < nsmall))) {
+          if ((ia < nsmall) | (ib < nsmall)) {
+            const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key);
+            gs_attempt(ia, nsmall, w.x, w.y, a_small, a_cst4, a_lrow, m);
+            gs_attempt(ib, nsmall, w.z, w.w, a_small, a_cst4, a_lrow, m);
           }
         }
         __syncwarp();
-        // normalise in log space.  e_c = exp(l_c - m); A = sum e = 1 + A' with the max term kept out
+        // normalise in log space.  e_c = 2^(l_c - m); A = sum e = 1 + A' with the max term kept out
         // of the sum (log1p keeps ln A accurate when one class owns the sample);
-        // -sum_c x ln x = ln A - (sum_c e_c d_c) / A with d_c = l_c - m
+        // -sum_c x ln x = ln A - ln2 * (sum_c e_c d_c) / A with d_c = l_c - m (log2 units)
         float inv_a = 0.f;
         if (active) {
           if (!(m > -INFINITY)) m = 0.f;
           float ap = 0.f, bs = 0.f;
           int nzero = 0;
-          for (int c = 0; c < C; ++c) {
-            const float d = fmaxf(lbuf[c * kLStride + lane] - m, -200.f);
-            const float e = ex2_approx(d * kLog2e);
+          unsigned addr = a_lrow;
+          for (int c = 0; c < C; ++c, addr += kLStride * 4u) {
+            const float d = fmaxf(lds_f32(addr) - m, -300.f);
+            const float e = ex2_approx(d);
             if (d == 0.f) ++nzero; else ap += e;
             bs = fmaf(e, d, bs);
-            lbuf[c * kLStride + lane] = e;
+            sts_f32(addr, e);
           }
           if (nzero > 0) {
             ap += (float)(nzero - 1);
             inv_a = __fdividef(1.f, 1.f + ap);
-            ent_acc += log1pf(ap) - bs * inv_a;
+            ent_acc += log1pf(ap) - kLn2 * bs * inv_a;
           }
         } else {
-          for (int c = 0; c < C; ++c) lbuf[c * kLStride + lane] = 0.f;
+          unsigned addr = a_lrow;
+          for (int c = 0; c < C; ++c, addr += kLStride * 4u) sts_f32(addr, 0.f);
         }
         __syncwarp();
         // class sums over the 32 samples, transposed: lane = class, walk the samples
