@@ -17,8 +17,9 @@ constexpr size_t kSelSmem = kSelCap * 8 + 4096 * 4 + 40 * 4;
 constexpr int kGatherThreads = 128;
 
 // Softmax of one prior held in registers.  On return x[c] = exp(logit_c - max) (unnormalised),
-// inv = 1/sum, den = the Retina score denominator (sum_c p_c + 1e-20) + 1e-9 (1 for SSD) and
-// pfg = max foreground softmax probability.  p_c = x[c]*inv, score_c = p_c/den (Retina) or p_c.
+// inv = 1/sum, den = 1 / ((sum_c p_c + 1e-20) + 1e-9), the reciprocal of the Retina score denominator
+// (1 for SSD) and pfg = max foreground softmax probability.  p_c = x[c]*inv, score_c = p_c*den
+// (Retina; within 1 ulp of the reference's division) or p_c.
 // Summation is sequential in class order with explicitly rounded ops, so K1a (key) and K1c (row)
 // produce bit-identical values for the same prior.
 template <int C, int HEAD>
@@ -42,7 +43,7 @@ __device__ __forceinline__ void softmax_regs(float (&x)[C], float& inv, float& d
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) s = __fadd_rn(s, __fmul_rn(x[c], inv));
-    den = __fadd_rn(__fadd_rn(s, 1e-20f), 1e-9f);
+    den = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(s, 1e-20f), 1e-9f));
   } else {
     den = 1.f;
   }
@@ -65,7 +66,7 @@ __device__ __forceinline__ void softmax_stream(const float* __restrict__ src, si
     float s = 0.f;
     for (int c = 0; c < C; ++c)
       s = __fadd_rn(s, __fmul_rn(ex2_approx(fmaf(__ldg(src + c * stride), kLog2e, nml2)), inv));
-    den = __fadd_rn(__fadd_rn(s, 1e-20f), 1e-9f);
+    den = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(s, 1e-20f), 1e-9f));
   } else {
     den = 1.f;
   }
@@ -105,7 +106,7 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
     float m;
     softmax_stream<HEAD>(src, (size_t)L.HW, CC, m, inv, den, pfg);
   }
-  const float key = (HEAD == MEHHUA_HEAD_RETINA) ? __fdiv_rn(pfg, den) : pfg;
+  const float key = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pfg, den) : pfg;
   keys[(size_t)b * p.N + L.n_off + a * L.HW + hw] = key;
   if (pfg > p.fg_thr) level_fg[b * p.S + s] = 1;
 }
@@ -186,7 +187,7 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float pc = __fmul_rn(x[c], inv);
-        const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fdiv_rn(pc, den) : pc;
+        const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
         x[c] = sc;
         if (sc > best) { best = sc; arg = c; }
         if (c < NF && sc > p.score_thr) ++ncand;
@@ -200,7 +201,7 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
       for (int c = 0; c < CC; ++c) {
         const float e = ex2_approx(fmaf(__ldg(src + (size_t)c * L.HW), kLog2e, nml2));
         const float pc = __fmul_rn(e, inv);
-        const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fdiv_rn(pc, den) : pc;
+        const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
         srow[c] = sc;
         if (sc > best) { best = sc; arg = c; }
         if (c < NF && sc > p.score_thr) ++ncand;

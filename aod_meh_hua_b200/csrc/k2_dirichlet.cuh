@@ -63,33 +63,27 @@ __host__ __device__ inline size_t k2_warp_floats(int C) {
 }
 __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_warp_floats(C) * sizeof(float) + 1040 * sizeof(int); }
 
-// One Ahrens-Dieter GS attempt for the class at position i of the small-alpha list, branch-free.
-// Works in log2 units: on acceptance stores l2 = log2(gamma draw) and advances the cursor by 2.
+// One Ahrens-Dieter GS attempt for the class at position i of the small-alpha list, as straight-line
+// code (no branches, so the attempts of a lane's cursors interleave in the pipelines).  Works in
+// log2 units; returns whether the draw is accepted, its class and l2 = log2(gamma draw).
 //   p = b*U1;  p <= 1: x = p^(1/alpha), accept iff U2 <= exp(-x)
 //              p >  1: x = -ln((b-p)/alpha) >= 1, accept iff U2 <= x^(alpha-1)
 // both tests are done as log2(U2) <= rhs.
-__device__ __forceinline__ void gs_attempt(int& i, const int nsmall, const unsigned w0, const unsigned w1,
-                                           const unsigned s_small, const unsigned s_cst4, const unsigned lrow,
-                                           float& m) {
-  if (i < nsmall) {
-    const unsigned c = lds_u8(s_small + i);
-    const float4 k = lds_v4(s_cst4 + c * 16u);            // b*2^-32, 1/alpha, alpha-1, b
-    const float pp = (float)w0 * k.x;
-    const bool lo = pp <= 1.f;
-    const float q = lo ? pp : (k.w - pp) * k.y;
-    const float lq = lg2_approx(q);
-    const float l2a = lq * k.y;                           // log2 x, first branch
-    const float rhsa = -kLog2e * ex2_approx(l2a);         // log2 exp(-x)
-    const float l2b = lg2_approx(-kLn2 * lq);             // log2 x, second branch
-    const float rhsb = k.z * l2b;                         // log2 x^(alpha-1)
-    const float l2 = lo ? l2a : l2b;
-    const float rhs = lo ? rhsa : rhsb;
-    if (lg2_approx((float)w1) - 32.f <= rhs) {
-      sts_f32(lrow + c * (kLStride * 4u), l2);
-      m = fmaxf(m, l2);
-      i += 2;
-    }
-  }
+__device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const unsigned w0, const unsigned w1,
+                                           const unsigned s_small, const unsigned s_cst4, unsigned& c, float& l2) {
+  c = lds_u8(s_small + min(i, nsmall - 1));
+  const float4 k = lds_v4(s_cst4 + c * 16u);            // b*2^-32, 1/alpha, alpha-1, b
+  const float pp = (float)w0 * k.x;
+  const bool lo = pp <= 1.f;
+  const float q = lo ? pp : (k.w - pp) * k.y;
+  const float lq = lg2_approx(q);
+  const float l2a = lq * k.y;                           // log2 x, first branch
+  const float rhsa = -kLog2e * ex2_approx(l2a);         // log2 exp(-x)
+  const float l2b = lg2_approx(-kLn2 * lq);             // log2 x, second branch
+  const float rhsb = k.z * l2b;                         // log2 x^(alpha-1)
+  l2 = lo ? l2a : l2b;
+  const float rhs = lo ? rhsa : rhsb;
+  return (i < nsmall) & (lg2_approx((float)w1) - 32.f <= rhs);
 }
 
 __global__ void __launch_bounds__(kK2Threads)
@@ -227,11 +221,15 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         // never idles while a neighbour retries and the two attempts overlap in the pipelines.
         int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall;
         unsigned kcall = 0;
-        while (__any_sync(full, (ia < nsmall) | (ib < nsmall))) {
-          if ((ia < nsmall) | (ib < nsmall)) {
+        if (nsmall > 0) {
+          while (__any_sync(full, (ia < nsmall) | (ib < nsmall))) {
             const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key);
-            gs_attempt(ia, nsmall, w.x, w.y, a_small, a_cst4, a_lrow, m);
-            gs_attempt(ib, nsmall, w.z, w.w, a_small, a_cst4, a_lrow, m);
+            unsigned ca, cb;
+            float la, lb;
+            const bool oka = gs_attempt(ia, nsmall, w.x, w.y, a_small, a_cst4, ca, la);
+            const bool okb = gs_attempt(ib, nsmall, w.z, w.w, a_small, a_cst4, cb, lb);
+            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), la); m = fmaxf(m, la); ia += 2; }
+            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), lb); m = fmaxf(m, lb); ib += 2; }
           }
         }
         __syncwarp();

@@ -17,7 +17,9 @@ namespace mehhua {
 constexpr int kNmsThreads = 512;
 constexpr int kNmsCap = 2048;     // candidates held in shared memory per chunk
 constexpr int kNmsChunk = 1024;   // candidates requested per chunk
-constexpr size_t kNmsSmem = kNmsCap * 8 + 4096 * 4 + 40 * 4 + kNmsCap * 16 + kNmsCap + MEHHUA_MAX_DETS * 16;
+constexpr int kNmsSub = 256;      // candidates resolved per suppression-matrix block
+// buf | sbox | kept | hist (aliased by the 256x8-word suppression matrix) | sh | class ids | alive
+constexpr size_t kNmsSmem = kNmsCap * 8 + kNmsCap * 16 + MEHHUA_MAX_DETS * 16 + 4096 * 4 + 48 * 4 + kNmsCap * 2 + kNmsCap;
 
 // IoU of the greedy NMS: inter / (area_i + area_j - inter), areas without +1, all fp32-rounded.
 __device__ __forceinline__ float iou_nms(const float4 a, const float4 b) {
@@ -31,8 +33,11 @@ __device__ __forceinline__ float iou_nms(const float4 a, const float4 b) {
 
 // ------------------------------------------------------------------------------------------
 // K3a.  Candidates are visited in descending (score, then ascending flat index) order, in sorted
-// chunks pulled out of the unordered candidate list by block radix-select; the greedy pass stops
-// as soon as max_per_img detections are kept, so normally one chunk is enough.
+// chunks pulled out of the unordered candidate list by block radix-select.  Inside a chunk the
+// greedy pass works on blocks of 256 candidates: all threads fill a 256x256-bit suppression matrix
+// (boxes carry the per-class offset, so only same-class pairs can overlap), one warp then resolves
+// keep / suppress sequentially with word-wide mask updates, and the block's new detections
+// suppress the rest of the chunk in parallel.  The pass stops at max_per_img detections.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNmsThreads)
 k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restrict__ cand,
@@ -45,8 +50,10 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
   float4* sbox = reinterpret_cast<float4*>(buf + kNmsCap);                        // kNmsCap
   float4* kept = sbox + kNmsCap;                                                  // MAX_DETS
   int* hist = reinterpret_cast<int*>(kept + MEHHUA_MAX_DETS);                     // 4096
-  int* sh = hist + 4096;                                                          // 40
-  unsigned char* alive = reinterpret_cast<unsigned char*>(sh + 40);               // kNmsCap
+  unsigned* rowmask = reinterpret_cast<unsigned*>(hist);                          // [kNmsSub][8], aliases hist
+  int* sh = hist + 4096;                                                          // 48
+  unsigned short* scls = reinterpret_cast<unsigned short*>(sh + 48);              // kNmsCap
+  unsigned char* alive = reinterpret_cast<unsigned char*>(scls + kNmsCap);        // kNmsCap
 
   const int b = blockIdx.x;
   const int NF = p.num_fg;
@@ -55,45 +62,90 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)b * p.K;
   const float off_unit = (nc > 0) ? __fadd_rn(ord2f(cand_maxc[b]), 1.0f) : 0.f;
   auto get = [&](int i) -> unsigned long long { return __ldcg(cp + i); };
+  const int lane = threadIdx.x & 31;
 
-  int nk = 0, nobj = 0, processed = 0;
+  int nk = 0, processed = 0;
   unsigned long long hi = ~0ull;
   while (nk < p.max_per_img && processed < nc) {
     const int cnt = block_collect_topk<kNmsThreads, kNmsCap, 0>(get, nc, kNmsChunk, hi, buf, hist, sh, status);
     if (cnt == 0) break;
+    // offset boxes, class ids, suppression by detections kept from earlier chunks
     for (int i = threadIdx.x; i < cnt; i += kNmsThreads) {
       const unsigned flat = 0xffffffffu - (unsigned)(buf[i] & 0xffffffffull);
       const int r = flat / NF, c = flat - r * NF;
       const float4 o = bx[r];
       const float off = __fmul_rn((float)c, off_unit);
-      float4 sb = make_float4(__fadd_rn(o.x, off), __fadd_rn(o.y, off), __fadd_rn(o.z, off), __fadd_rn(o.w, off));
+      const float4 sb = make_float4(__fadd_rn(o.x, off), __fadd_rn(o.y, off), __fadd_rn(o.z, off), __fadd_rn(o.w, off));
       unsigned char ok = 1;
       for (int q = 0; q < nk; ++q)
         if (iou_nms(kept[q], sb) > p.nms_iou) { ok = 0; break; }
       sbox[i] = sb;
+      scls[i] = (unsigned short)c;
       alive[i] = ok;
     }
     __syncthreads();
-    for (int i = 0; i < cnt; ++i) {
-      if (!alive[i]) continue;          // uniform: alive[] only changes before a barrier
-      const float4 bi = sbox[i];
-      if (threadIdx.x == 0) {
-        const unsigned long long e = buf[i];
-        const unsigned flat = 0xffffffffu - (unsigned)(e & 0xffffffffull);
-        const int r = flat / NF, c = flat - r * NF;
-        const float sc = __uint_as_float((unsigned)(e >> 32));
-        const float4 o = bx[r];
-        float* d = dets + ((size_t)b * p.max_per_img + nk) * 5;
-        d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w; d[4] = sc;
-        det_labels[(size_t)b * p.max_per_img + nk] = c;
-        det_flat[(size_t)b * p.max_per_img + nk] = (int)flat;
-        kept[nk] = bi;
-        if (sc > p.obj_thr) ++nobj;
+    for (int sb0 = 0; sb0 < cnt && nk < p.max_per_img; sb0 += kNmsSub) {
+      const int nsb = min(kNmsSub, cnt - sb0);
+      // (1) suppression matrix of the block: thread = (row, half of the columns)
+      {
+        const int ri = threadIdx.x & (kNmsSub - 1), half = threadIdx.x >> 8;
+        unsigned wd[4] = {0u, 0u, 0u, 0u};
+        if (ri < nsb && alive[sb0 + ri]) {
+          const float4 bi = sbox[sb0 + ri];
+          const unsigned short ci = scls[sb0 + ri];
+#pragma unroll
+          for (int wq = 0; wq < 4; ++wq) {
+            const int j0 = (half * 4 + wq) * 32;
+            unsigned bits = 0u;
+            for (int j = max(j0, ri + 1); j < min(j0 + 32, nsb); ++j)
+              if (scls[sb0 + j] == ci && iou_nms(bi, sbox[sb0 + j]) > p.nms_iou) bits |= 1u << (j - j0);
+            wd[wq] = bits;
+          }
+        }
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) rowmask[ri * 8 + half * 4 + wq] = wd[wq];
       }
-      ++nk;
-      if (nk >= p.max_per_img) break;
-      for (int j = i + 1 + threadIdx.x; j < cnt; j += kNmsThreads)
-        if (alive[j] && iou_nms(bi, sbox[j]) > p.nms_iou) alive[j] = 0;
+      __syncthreads();
+      // (2) sequential resolve by warp 0: lane l < 8 owns alive word l of the block
+      const int nk_before = nk;
+      if (threadIdx.x < 32) {
+        unsigned aw = 0u;
+        if (lane < 8)
+          for (int j = 0; j < 32; ++j) {
+            const int i = lane * 32 + j;
+            if (i < nsb && alive[sb0 + i]) aw |= 1u << j;
+          }
+        int k = nk;
+        for (int i = 0; i < nsb && k < p.max_per_img; ++i) {
+          const unsigned wv = __shfl_sync(0xffffffffu, aw, i >> 5);
+          if (!((wv >> (i & 31)) & 1u)) continue;
+          if (lane < 8) aw &= ~rowmask[i * 8 + lane];
+          if (lane == 0) {
+            const unsigned long long e = buf[sb0 + i];
+            const unsigned flat = 0xffffffffu - (unsigned)(e & 0xffffffffull);
+            const int r = flat / NF;
+            const float4 o = bx[r];
+            float* d = dets + ((size_t)b * p.max_per_img + k) * 5;
+            d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w; d[4] = __uint_as_float((unsigned)(e >> 32));
+            det_labels[(size_t)b * p.max_per_img + k] = (int)scls[sb0 + i];
+            det_flat[(size_t)b * p.max_per_img + k] = (int)flat;
+            kept[k] = sbox[sb0 + i];
+          }
+          ++k;
+        }
+        if (lane == 0) sh[44] = k;
+      }
+      __syncthreads();
+      nk = sh[44];
+      // (3) the block's new detections suppress the rest of the chunk
+      if (nk < p.max_per_img && nk > nk_before) {
+        for (int j = sb0 + nsb + threadIdx.x; j < cnt; j += kNmsThreads) {
+          if (!alive[j]) continue;
+          const float4 bj = sbox[j];
+          for (int q = nk_before; q < nk; ++q)
+            if (iou_nms(kept[q], bj) > p.nms_iou) { alive[j] = 0; break; }
+        }
+      }
       __syncthreads();
     }
     processed += cnt;
@@ -101,17 +153,25 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0) {
+    int nobj = 0;
+    for (int k = 0; k < nk; ++k)
+      if (dets[((size_t)b * p.max_per_img + k) * 5 + 4] > p.obj_thr) ++nobj;
     n_det[b] = nk;
     n_obj[b] = nobj;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// K3b.  One block per image.  For every foreground row (row max > fg_thr, level flagged FG) test
-// IoU > cluster_iou against each object; pairs are emitted in row-major (row, object) order - the
-// order of FG_pos_bbox.nonzero() - by an ordered block scan, level by level.
+// K3b.  One block per image, rows processed in chunks of 1024 (row order = level order):
+//   (a) ordered compaction of the chunk's foreground rows (row max > fg_thr, level flagged FG);
+//   (b) one warp per foreground row, lane = object: IoU > cluster_iou -> ballot -> bit mask;
+//   (c) block scan of the per-row pair counts;  (d) pairs emitted in row-major (row, object)
+//   order - the order of FG_pos_bbox.nonzero().
+// Afterwards warp s averages lambda over level s's pairs (duplicates counted) in a fixed order.
 // ------------------------------------------------------------------------------------------
 constexpr int kPairThreads = 256;
+constexpr int kPairChunk = 4 * kPairThreads;
+constexpr int kPairWords = MEHHUA_MAX_DETS / 32;
 
 __global__ void __launch_bounds__(kPairThreads)
 k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes,
@@ -121,97 +181,133 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
                  int* __restrict__ pair_row, int* __restrict__ pair_obj, int* __restrict__ pair_cls,
                  int* __restrict__ pair_off, float* __restrict__ lam_mean, unsigned* __restrict__ status) {
   __shared__ float4 obox[MEHHUA_MAX_DETS];
-  __shared__ int wsum[32];
-  __shared__ float fsum[32];
-  __shared__ int s_total;
+  __shared__ unsigned mask[kPairChunk * kPairWords];   // 32 KB
+  __shared__ int fg_idx[kPairChunk];
+  __shared__ int fg_cnt[kPairChunk];
+  __shared__ int wsum[40];
+  __shared__ int lvl_cnt[kMaxLevels];
+  __shared__ int lvl_fg[kMaxLevels];
   const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nobj = n_obj[b];
+  const int nwords = (nobj + 31) >> 5;
   for (int o = threadIdx.x; o < nobj; o += kPairThreads) {
     const float* d = dets + ((size_t)b * p.max_per_img + o) * 5;
     obox[o] = make_float4(d[0], d[1], d[2], d[3]);
   }
+  if (threadIdx.x < kMaxLevels) {
+    lvl_cnt[threadIdx.x] = 0;
+    lvl_fg[threadIdx.x] = (threadIdx.x < p.S) ? level_fg[b * p.S + threadIdx.x] : 0;
+  }
   __syncthreads();
   const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)b * p.K;
+  const float* rmax = row_max + (size_t)b * p.K;
   int running = 0;
-  for (int s = 0; s < p.S; ++s) {
-    const LevelDev& L = p.lv[s];
-    const int start = running;
-    float lam_acc = 0.f;
-    if (nobj > 0 && level_fg[b * p.S + s]) {
-      for (int base = 0; base < L.k; base += kPairThreads) {
-        const int i = base + threadIdx.x;
-        const int r = L.k_off + i;
-        unsigned words[MEHHUA_MAX_DETS / 32];
+  if (nobj > 0) {
+    for (int base = 0; base < p.K; base += kPairChunk) {
+      // (a) ordered compaction of foreground rows
+      const int r0 = base + 4 * threadIdx.x;
+      int flags = 0;
 #pragma unroll
-        for (int w = 0; w < MEHHUA_MAX_DETS / 32; ++w) words[w] = 0u;
-        int cnt = 0;
-        if (i < L.k && row_max[(size_t)b * p.K + r] > p.fg_thr) {
-          const float4 rb = bx[r];
-          const float area = __fmul_rn(__fsub_rn(rb.z, rb.x), __fsub_rn(rb.w, rb.y));
-#pragma unroll
-          for (int w = 0; w < MEHHUA_MAX_DETS / 32; ++w) {
-            unsigned bits = 0u;
-            for (int j = 0; j < 32; ++j) {
-              const int o = w * 32 + j;
-              if (o < nobj && iou_overlaps(rb, area, obox[o]) > p.cluster_iou) bits |= 1u << j;
-            }
-            words[w] = bits;
-            cnt += __popc(bits);
-          }
-        }
-        const int incl = block_incl_scan<kPairThreads>(cnt, wsum);
-        if (threadIdx.x == kPairThreads - 1) s_total = incl;
-        if (cnt > 0) {
-          int pos = running + incl - cnt;
-          const int cls = row_argmax[(size_t)b * p.K + r];
-#pragma unroll
-          for (int w = 0; w < MEHHUA_MAX_DETS / 32; ++w) {
-            unsigned bits = words[w];
-            while (bits) {
-              const int j = __ffs(bits) - 1;
-              bits &= bits - 1;
-              if (pos < p.pair_cap) {
-                const size_t q = (size_t)b * p.pair_cap + pos;
-                pair_row[q] = r; pair_obj[q] = w * 32 + j; pair_cls[q] = cls;
-              }
-              ++pos;
-            }
-          }
-          lam_acc = __fmaf_rn((float)cnt, lam_rows[(size_t)b * p.K + r], lam_acc);
-        }
-        __syncthreads();
-        running += s_total;
-        __syncthreads();
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j;
+        if (r < p.K && rmax[r] > p.fg_thr && lvl_fg[level_of_row(p, r)]) flags |= 1 << j;
       }
+      const int nf = __popc(flags);
+      const int incl = block_incl_scan<kPairThreads>(nf, wsum);
+      if (threadIdx.x == kPairThreads - 1) wsum[32] = incl;
+      {
+        int pos = incl - nf;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (flags & (1 << j)) fg_idx[pos++] = r0 + j;
+      }
+      __syncthreads();
+      const int nfg = wsum[32];
+      // (b) IoU masks: warp per foreground row, lane = object
+      for (int e = w; e < nfg; e += kPairThreads / 32) {
+        const float4 rb = bx[fg_idx[e]];
+        const float area = __fmul_rn(__fsub_rn(rb.z, rb.x), __fsub_rn(rb.w, rb.y));
+        int cnt = 0;
+        for (int gq = 0; gq < nwords; ++gq) {
+          const int o = gq * 32 + lane;
+          const bool hit = (o < nobj) && iou_overlaps(rb, area, obox[min(o, nobj - 1)]) > p.cluster_iou;
+          const unsigned bits = __ballot_sync(0xffffffffu, hit);
+          if (lane == 0) mask[e * kPairWords + gq] = bits;
+          cnt += __popc(bits);
+        }
+        if (lane == 0) fg_cnt[e] = cnt;
+      }
+      __syncthreads();
+      // (c) scan of pair counts, four consecutive entries per thread
+      const int e0 = 4 * threadIdx.x;
+      int c4 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < nfg) c4 += fg_cnt[e0 + j];
+      const int incl2 = block_incl_scan<kPairThreads>(c4, wsum);
+      if (threadIdx.x == kPairThreads - 1) wsum[33] = incl2;
+      // (d) emit
+      int pos = running + incl2 - c4;
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j;
+        if (e >= nfg) break;
+        const int cnt = fg_cnt[e];
+        if (cnt == 0) continue;
+        const int r = fg_idx[e];
+        const int cls = row_argmax[(size_t)b * p.K + r];
+        atomicAdd(&lvl_cnt[level_of_row(p, r)], cnt);
+        for (int gq = 0; gq < nwords; ++gq) {
+          unsigned bits = mask[e * kPairWords + gq];
+          while (bits) {
+            const int jj = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < p.pair_cap) {
+              const size_t q = (size_t)b * p.pair_cap + pos;
+              pair_row[q] = r; pair_obj[q] = gq * 32 + jj; pair_cls[q] = cls;
+            }
+            ++pos;
+          }
+        }
+      }
+      __syncthreads();
+      running += wsum[33];
+      __syncthreads();
     }
-    // mean lambda over the level's pairs (duplicates counted), fixed reduction tree
-    float v = lam_acc;
+  }
+  // per-level offsets (levels are contiguous in row order, so pairs are too)
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int s = 0; s < p.S; ++s) {
+      pair_off[b * (p.S + 1) + s] = min(acc, p.pair_cap);
+      acc += lvl_cnt[s];
+    }
+    pair_off[b * (p.S + 1) + p.S] = min(acc, p.pair_cap);
+    if (acc > p.pair_cap) atomicOr(status, MEHHUA_ST_PAIR_OVERFLOW);
+  }
+  __syncthreads();
+  // mean lambda over each level's pairs: warp s, lane-strided partial sums + fixed shuffle tree
+  for (int s = w; s < p.S; s += kPairThreads / 32) {
+    const int a = pair_off[b * (p.S + 1) + s], e = pair_off[b * (p.S + 1) + s + 1];
+    float v = 0.f;
+    for (int q = a + lane; q < e; q += 32)
+      v += lam_rows[(size_t)b * p.K + pair_row[(size_t)b * p.pair_cap + q]];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) fsum[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-      for (int w = 0; w < kPairThreads / 32; ++w) tot += fsum[w];
-      const int np = running - start;
-      lam_mean[b * p.S + s] = np > 0 ? __fdiv_rn(tot, (float)np) : 0.f;
-      pair_off[b * (p.S + 1) + s] = min(start, p.pair_cap);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    pair_off[b * (p.S + 1) + p.S] = min(running, p.pair_cap);
-    if (running > p.pair_cap) atomicOr(status, MEHHUA_ST_PAIR_OVERFLOW);
+    if (lane == 0) lam_mean[b * p.S + s] = (e > a) ? __fdiv_rn(v, (float)(e - a)) : 0.f;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// K3c.  One block per image, one warp per object at a time.  Lane l owns the (level, class) cells
-// with class % 32 == l and walks the image's ordered pair list, so every cell is accumulated by a
-// single thread in pair order (deterministic, no atomics).  Then class -> level -> object
-// aggregation with Sum / Avg / Max selected per level of the hierarchy.
+// K3c.  One block per image.  The image's ordered pair list is grouped by (object, level, class):
+// pairs are sorted by that key (bitonic sort in shared memory, pair ordinal as tie-break so every
+// group is summed in pair order - deterministic), run leaders produce the group means, and one
+// thread walks the sorted group table doing class -> level -> object aggregation with Sum / Avg /
+// Max selected per level of the hierarchy.  Images with more than kHuaCap pairs take a slower
+// path (one warp per object scanning the pair list) with the same arithmetic.
 // ------------------------------------------------------------------------------------------
 constexpr int kHuaThreads = 256;
+constexpr int kHuaCap = 4096;
 
 __device__ __forceinline__ float agg_combine(int op, float acc, float v) {
   return op == MEHHUA_AGG_MAX ? fmaxf(acc, v) : acc + v;
@@ -220,18 +316,22 @@ __device__ __forceinline__ float agg_finish(int op, float acc, int n) {
   return op == MEHHUA_AGG_AVG ? __fdiv_rn(acc, (float)n) : acc;
 }
 
+__host__ __device__ inline size_t k3c_smem_bytes(int S, int C) {
+  const size_t fast = (size_t)kHuaCap * 8 + (size_t)kHuaCap * 8;                 // sort keys + group (key, mean)
+  const size_t slow = (size_t)(kHuaThreads / 32) * S * C * 8 + MEHHUA_MAX_DETS * 8;
+  return (fast > slow ? fast : slow) + ((C + 31) / 32) * 4 + 64 * 4;
+}
+
 __global__ void __launch_bounds__(kHuaThreads)
 k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
                const int* __restrict__ pair_obj, const int* __restrict__ pair_cls,
                const int* __restrict__ pair_off, const float* __restrict__ pair_unc,
                const int* __restrict__ n_obj, float* __restrict__ image_scores) {
   extern __shared__ __align__(16) unsigned char k3c_smem[];
-  const int cells = p.S * p.C;
-  float* csum = reinterpret_cast<float*>(k3c_smem);                 // [warps][cells]
-  int* ccnt = reinterpret_cast<int*>(csum + (kHuaThreads / 32) * cells);
-  float* oval = reinterpret_cast<float*>(ccnt + (kHuaThreads / 32) * cells);   // [MAX_DETS]
-  int* ohas = reinterpret_cast<int*>(oval + MEHHUA_MAX_DETS);                   // [MAX_DETS]
-  unsigned* cls_seen = reinterpret_cast<unsigned*>(ohas + MEHHUA_MAX_DETS);     // [(C+31)/32]
+  const size_t fast = (size_t)kHuaCap * 16;
+  const size_t slow = (size_t)(kHuaThreads / 32) * p.S * p.C * 8 + MEHHUA_MAX_DETS * 8;
+  unsigned* cls_seen = reinterpret_cast<unsigned*>(k3c_smem + (fast > slow ? fast : slow));   // [(C+31)/32]
+  int* sh = reinterpret_cast<int*>(cls_seen + (p.C + 31) / 32);                               // 64 ints
 
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -242,63 +342,140 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
   const int* pcls = pair_cls + (size_t)b * p.pair_cap;
   const float* punc = pair_unc + (size_t)b * p.pair_cap * 3;
   for (int i = threadIdx.x; i < (p.C + 31) / 32; i += kHuaThreads) cls_seen[i] = 0u;
-  for (int i = threadIdx.x; i < MEHHUA_MAX_DETS; i += kHuaThreads) { oval[i] = 0.f; ohas[i] = 0; }
   __syncthreads();
-  float* ms = csum + w * cells;
-  int* mc = ccnt + w * cells;
-  for (int o = w; o < nobj; o += kHuaThreads / 32) {
-    for (int i = lane; i < cells; i += 32) { ms[i] = 0.f; mc[i] = 0; }
-    __syncwarp();
-    for (int q = 0; q < np; ++q) {
-      if (pobj[q] != o) continue;                 // warp-uniform
-      const int cls = pcls[q];
-      if ((cls & 31) == lane) {
-        const int cell = level_of_row(p, prow[q]) * p.C + cls;
-        ms[cell] += punc[q * 3 + 2];              // epistemic
-        mc[cell] += 1;
+  float out = 0.f;
+
+  if (np <= kHuaCap) {
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(k3c_smem);           // [kHuaCap]
+    unsigned* gkey = reinterpret_cast<unsigned*>(keys + kHuaCap);                          // [kHuaCap]
+    float* gval = reinterpret_cast<float*>(gkey + kHuaCap);                                // [kHuaCap]
+    int n2 = 1;
+    while (n2 < np) n2 <<= 1;
+    // inverted composite so the descending sort yields ascending (group key, pair ordinal)
+    for (int q = threadIdx.x; q < n2; q += kHuaThreads) {
+      unsigned long long e = 0ull;
+      if (q < np) {
+        const unsigned gk = (unsigned)((pobj[q] * p.S + level_of_row(p, prow[q])) * p.C + pcls[q]);
+        e = ~(((unsigned long long)gk << 32) | (unsigned)q);
       }
+      keys[q] = e;
     }
-    __syncwarp();
-    // class aggregation per level, then level aggregation (lane 0 keeps the running value)
-    float lvl_acc = 0.f;
-    int lvl_n = 0;
-    for (int s = 0; s < p.S; ++s) {
-      float acc = (p.agg_class == MEHHUA_AGG_MAX) ? -FLT_MAX : 0.f;
-      int n = 0;
-      for (int c = lane; c < p.C; c += 32) {
-        const int k = mc[s * p.C + c];
-        if (k > 0) {
-          acc = agg_combine(p.agg_class, acc, __fdiv_rn(ms[s * p.C + c], (float)k));
-          ++n;
-          atomicOr(&cls_seen[c >> 5], 1u << (c & 31));
+    __syncthreads();
+    block_bitonic_desc<kHuaThreads>(keys, n2);
+    // run leaders -> group means, written in key order
+    int running = 0;
+    for (int base = 0; base < np; base += kHuaThreads) {
+      const int i = base + threadIdx.x;
+      unsigned gk = 0u;
+      bool leader = false;
+      if (i < np) {
+        gk = (unsigned)((~keys[i]) >> 32);
+        leader = (i == 0) || gk != (unsigned)((~keys[i - 1]) >> 32);
+      }
+      const int incl = block_incl_scan<kHuaThreads>(leader ? 1 : 0, sh);
+      if (threadIdx.x == kHuaThreads - 1) sh[40] = incl;
+      if (leader) {
+        float sum = 0.f;
+        int cnt = 0;
+        for (int j = i; j < np; ++j) {
+          const unsigned long long e = ~keys[j];
+          if ((unsigned)(e >> 32) != gk) break;
+          sum += punc[(unsigned)(e & 0xffffffffull) * 3 + 2];     // epistemic, in pair order
+          ++cnt;
+        }
+        const int gi = running + incl - 1;
+        gkey[gi] = gk;
+        gval[gi] = __fdiv_rn(sum, (float)cnt);
+        const unsigned cls = gk % (unsigned)p.C;
+        atomicOr(&cls_seen[cls >> 5], 1u << (cls & 31));
+      }
+      __syncthreads();
+      running += sh[40];
+      __syncthreads();
+    }
+    // one thread walks the (object, level, class)-sorted group table
+    if (threadIdx.x == 0) {
+      const int ng = running;
+      float oacc = 0.f;
+      int on = 0;
+      int g = 0;
+      while (g < ng) {
+        const unsigned obj = gkey[g] / (unsigned)(p.S * p.C);
+        float lacc = 0.f;
+        int ln = 0;
+        while (g < ng && gkey[g] / (unsigned)(p.S * p.C) == obj) {
+          const unsigned ol = gkey[g] / (unsigned)p.C;
+          float cacc = (p.agg_class == MEHHUA_AGG_MAX) ? -FLT_MAX : 0.f;
+          int cn = 0;
+          while (g < ng && gkey[g] / (unsigned)p.C == ol) { cacc = agg_combine(p.agg_class, cacc, gval[g]); ++cn; ++g; }
+          const float cv = agg_finish(p.agg_class, cacc, cn);
+          lacc = (ln == 0) ? cv : agg_combine(p.agg_scale, lacc, cv);
+          ++ln;
+        }
+        const float lv = agg_finish(p.agg_scale, lacc, ln);
+        oacc = (on == 0) ? lv : agg_combine(p.agg_object, oacc, lv);
+        ++on;
+      }
+      out = on > 0 ? agg_finish(p.agg_object, oacc, on) : 0.f;
+    }
+  } else {
+    const int cells = p.S * p.C;
+    float* csum = reinterpret_cast<float*>(k3c_smem);                 // [warps][cells]
+    int* ccnt = reinterpret_cast<int*>(csum + (kHuaThreads / 32) * cells);
+    float* oval = reinterpret_cast<float*>(ccnt + (kHuaThreads / 32) * cells);   // [MAX_DETS]
+    int* ohas = reinterpret_cast<int*>(oval + MEHHUA_MAX_DETS);                   // [MAX_DETS]
+    for (int i = threadIdx.x; i < MEHHUA_MAX_DETS; i += kHuaThreads) { oval[i] = 0.f; ohas[i] = 0; }
+    __syncthreads();
+    float* ms = csum + w * cells;
+    int* mc = ccnt + w * cells;
+    for (int o = w; o < nobj; o += kHuaThreads / 32) {
+      for (int i = lane; i < cells; i += 32) { ms[i] = 0.f; mc[i] = 0; }
+      __syncwarp();
+      for (int q = 0; q < np; ++q) {
+        if (pobj[q] != o) continue;                 // warp-uniform
+        const int cls = pcls[q];
+        if ((cls & 31) == lane) {
+          const int cell = level_of_row(p, prow[q]) * p.C + cls;
+          ms[cell] += punc[q * 3 + 2];
+          mc[cell] += 1;
         }
       }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        const float oa = __shfl_xor_sync(0xffffffffu, acc, d);
-        const int on = __shfl_xor_sync(0xffffffffu, n, d);
-        acc = agg_combine(p.agg_class, acc, oa);
-        n += on;
+      __syncwarp();
+      if (lane == 0) {       // sequential class -> level aggregation, same order as the fast path
+        float lacc = 0.f;
+        int ln = 0;
+        for (int s = 0; s < p.S; ++s) {
+          float cacc = (p.agg_class == MEHHUA_AGG_MAX) ? -FLT_MAX : 0.f;
+          int cn = 0;
+          for (int c = 0; c < p.C; ++c) {
+            const int k = mc[s * p.C + c];
+            if (k > 0) {
+              cacc = agg_combine(p.agg_class, cacc, __fdiv_rn(ms[s * p.C + c], (float)k));
+              ++cn;
+              atomicOr(&cls_seen[c >> 5], 1u << (c & 31));
+            }
+          }
+          if (cn > 0) {
+            const float cv = agg_finish(p.agg_class, cacc, cn);
+            lacc = (ln == 0) ? cv : agg_combine(p.agg_scale, lacc, cv);
+            ++ln;
+          }
+        }
+        if (ln > 0) { oval[o] = agg_finish(p.agg_scale, lacc, ln); ohas[o] = 1; }
       }
-      if (n > 0) {
-        const float v = agg_finish(p.agg_class, acc, n);
-        lvl_acc = (lvl_n == 0) ? v : agg_combine(p.agg_scale, lvl_acc, v);
-        ++lvl_n;
-      }
+      __syncwarp();
     }
-    if (lane == 0 && lvl_n > 0) {
-      oval[o] = agg_finish(p.agg_scale, lvl_acc, lvl_n);
-      ohas[o] = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float acc = 0.f;
+      int n = 0;
+      for (int o = 0; o < nobj; ++o)
+        if (ohas[o]) { acc = (n == 0) ? oval[o] : agg_combine(p.agg_object, acc, oval[o]); ++n; }
+      out = n > 0 ? agg_finish(p.agg_object, acc, n) : 0.f;
     }
-    __syncwarp();
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float acc = 0.f;
-    int n = 0;
-    for (int o = 0; o < nobj; ++o)
-      if (ohas[o]) { acc = (n == 0) ? oval[o] : agg_combine(p.agg_object, acc, oval[o]); ++n; }
-    float out = n > 0 ? agg_finish(p.agg_object, acc, n) : 0.f;
     if (p.cls_w) {
       int k = 0;
       for (int i = 0; i < (p.C + 31) / 32; ++i) k += __popc(cls_seen[i]);

@@ -281,7 +281,7 @@ int launch_hua(const Plan& p, const mehhua_buffers_t* o, cudaStream_t st) {
   if (!o || !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->pair_unc || !o->n_obj ||
       !o->image_scores)
     return arg_fail("null HUA buffer");
-  const size_t smem = (size_t)(kHuaThreads / 32) * p.S * p.C * 8 + MEHHUA_MAX_DETS * 8 + ((p.C + 31) / 32) * 4;
+  const size_t smem = k3c_smem_bytes(p.S, p.C);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K3c shared-memory layout");
   static size_t attr = 0;
   if (smem > attr) {
