@@ -147,9 +147,14 @@ __device__ int block_collect_topk(Get get, int n, int k, unsigned long long hi,
     const int shift = kDigitShift[SCHED][pass], bits = kDigitBits[SCHED][pass], bins = 1 << bits;
     for (int i = threadIdx.x; i < bins; i += THREADS) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-      const unsigned long long e = get(i);
-      if (e != 0ull && e < hi && (e & mask) == prefix) atomicAdd(&hist[(int)((e >> shift) & (bins - 1))], 1);
+    for (int i0 = threadIdx.x; i0 < n; i0 += THREADS * 4) {   // four independent loads in flight
+      unsigned long long e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * THREADS; e[u] = (i < n) ? get(i) : 0ull; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e[u] != 0ull && e[u] < hi && (e[u] & mask) == prefix)
+          atomicAdd(&hist[(int)((e[u] >> shift) & (bins - 1))], 1);
     }
     __syncthreads();
     // thread t owns the t-th highest chunk of bins; scan chunk sums from the top
@@ -182,12 +187,16 @@ __device__ int block_collect_topk(Get get, int n, int k, unsigned long long hi,
   // compaction of every e in [prefix, hi)
   if (threadIdx.x == 0) sh[36] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += THREADS) {
-    const unsigned long long e = get(i);
-    if (e != 0ull && e < hi && e >= prefix) {
-      const int pos = atomicAdd(&sh[36], 1);
-      if (pos < CAP) buf[pos] = e;
-    }
+  for (int i0 = threadIdx.x; i0 < n; i0 += THREADS * 4) {
+    unsigned long long e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * THREADS; e[u] = (i < n) ? get(i) : 0ull; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e[u] != 0ull && e[u] < hi && e[u] >= prefix) {
+        const int pos = atomicAdd(&sh[36], 1);
+        if (pos < CAP) buf[pos] = e[u];
+      }
   }
   __syncthreads();
   int cnt = sh[36];

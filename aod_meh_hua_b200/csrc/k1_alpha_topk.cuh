@@ -112,7 +112,7 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
 }
 
 // ------------------------------------------------------------------------------------------
-// K1b: per (image, level) top-k of the keys, sorted descending (ties: lower prior index first).
+// K1b: per (image, level) top-k of the keys, sorted descending (exact ties: lower anchor, then lower position).
 // grid = (S, B); levels without an active top-k return immediately.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSelThreads)
@@ -126,19 +126,22 @@ k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys
   const LevelDev& L = p.lv[s];
   if (!L.topk) return;
   const float* kp = keys + (size_t)b * p.N + L.n_off;
-  const int HW = L.HW, A = L.A;
+  // composite = key bits << 32 | ~position, position j = a*HW + hw (the key array is anchor-major):
+  // exact key ties go to the lower position.  The prior index n = hw*A + a is only rebuilt for
+  // the k winners.
   auto get = [&](int j) -> unsigned long long {
     unsigned kb = __float_as_uint(__ldcg(kp + j));
     if (kb > 0x3fffffffu) kb = (kb & 0x80000000u) ? 0u : 0x3fffffffu;   // negatives / >= 2.0 / NaN
-    const int a = j / HW;
-    const int n = (j - a * HW) * A + a;
-    return ((unsigned long long)kb << 32) | (unsigned long long)(0xffffffffu - (unsigned)n);
+    return ((unsigned long long)kb << 32) | (unsigned long long)(0xffffffffu - (unsigned)j);
   };
   const int cnt = block_collect_topk<kSelThreads, kSelCap, 0>(get, L.n, L.k, ~0ull, buf, hist, sh, status);
   int* out = topk_idx + (size_t)b * p.K + L.k_off;
   const int k = min(L.k, cnt);
-  for (int i = threadIdx.x; i < k; i += kSelThreads)
-    out[i] = (int)(0xffffffffu - (unsigned)(buf[i] & 0xffffffffull));
+  for (int i = threadIdx.x; i < k; i += kSelThreads) {
+    const int j = (int)(0xffffffffu - (unsigned)(buf[i] & 0xffffffffull));
+    const int a = j / L.HW;
+    out[i] = (j - a * L.HW) * L.A + a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

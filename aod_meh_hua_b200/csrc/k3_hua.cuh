@@ -19,7 +19,7 @@ constexpr int kNmsCap = 2048;     // candidates held in shared memory per chunk
 constexpr int kNmsChunk = 1024;   // candidates requested per chunk
 constexpr int kNmsSub = 256;      // candidates resolved per suppression-matrix block
 // buf | sbox | kept | hist (aliased by the 256x8-word suppression matrix) | sh | class ids | alive
-constexpr size_t kNmsSmem = kNmsCap * 8 + kNmsCap * 16 + MEHHUA_MAX_DETS * 16 + 4096 * 4 + 48 * 4 + kNmsCap * 2 + kNmsCap;
+constexpr size_t kNmsSmem = kNmsCap * 8 + kNmsCap * 16 + MEHHUA_MAX_DETS * 16 + 4096 * 4 + 48 * 4 + kNmsCap * 2 + kNmsCap + MEHHUA_MAX_DETS * 2;
 
 // IoU of the greedy NMS: inter / (area_i + area_j - inter), areas without +1, all fp32-rounded.
 __device__ __forceinline__ float iou_nms(const float4 a, const float4 b) {
@@ -54,6 +54,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
   int* sh = hist + 4096;                                                          // 48
   unsigned short* scls = reinterpret_cast<unsigned short*>(sh + 48);              // kNmsCap
   unsigned char* alive = reinterpret_cast<unsigned char*>(scls + kNmsCap);        // kNmsCap
+  unsigned short* kept_idx = reinterpret_cast<unsigned short*>(alive + kNmsCap);  // MAX_DETS
 
   const int b = blockIdx.x;
   const int NF = p.num_fg;
@@ -66,6 +67,8 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
 
   int nk = 0, processed = 0;
   unsigned long long hi = ~0ull;
+  if (threadIdx.x == 0) sh[45] = 0;      // objects (detections above obj_thr); sh[0..36] belong to the select
+  __syncthreads();
   while (nk < p.max_per_img && processed < nc) {
     const int cnt = block_collect_topk<kNmsThreads, kNmsCap, 0>(get, nc, kNmsChunk, hi, buf, hist, sh, status);
     if (cnt == 0) break;
@@ -120,23 +123,25 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
           const unsigned wv = __shfl_sync(0xffffffffu, aw, i >> 5);
           if (!((wv >> (i & 31)) & 1u)) continue;
           if (lane < 8) aw &= ~rowmask[i * 8 + lane];
-          if (lane == 0) {
-            const unsigned long long e = buf[sb0 + i];
-            const unsigned flat = 0xffffffffu - (unsigned)(e & 0xffffffffull);
-            const int r = flat / NF;
-            const float4 o = bx[r];
-            float* d = dets + ((size_t)b * p.max_per_img + k) * 5;
-            d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w; d[4] = __uint_as_float((unsigned)(e >> 32));
-            det_labels[(size_t)b * p.max_per_img + k] = (int)scls[sb0 + i];
-            det_flat[(size_t)b * p.max_per_img + k] = (int)flat;
-            kept[k] = sbox[sb0 + i];
-          }
+          if (lane == 0) { kept[k] = sbox[sb0 + i]; kept_idx[k] = (unsigned short)(sb0 + i); }
           ++k;
         }
         if (lane == 0) sh[44] = k;
       }
       __syncthreads();
       nk = sh[44];
+      // the new detections are written out by one thread each (their box loads overlap)
+      for (int k = nk_before + threadIdx.x; k < nk; k += kNmsThreads) {
+        const unsigned long long e = buf[kept_idx[k]];
+        const unsigned flat = 0xffffffffu - (unsigned)(e & 0xffffffffull);
+        const int r = flat / NF;
+        const float4 o = bx[r];
+        float* d = dets + ((size_t)b * p.max_per_img + k) * 5;
+        d[0] = o.x; d[1] = o.y; d[2] = o.z; d[3] = o.w; d[4] = __uint_as_float((unsigned)(e >> 32));
+        det_labels[(size_t)b * p.max_per_img + k] = (int)(flat - r * NF);
+        det_flat[(size_t)b * p.max_per_img + k] = (int)flat;
+        if (d[4] > p.obj_thr) atomicAdd(&sh[45], 1);
+      }
       // (3) the block's new detections suppress the rest of the chunk
       if (nk < p.max_per_img && nk > nk_before) {
         for (int j = sb0 + nsb + threadIdx.x; j < cnt; j += kNmsThreads) {
@@ -152,12 +157,10 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
     hi = buf[cnt - 1];
     __syncthreads();
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    int nobj = 0;
-    for (int k = 0; k < nk; ++k)
-      if (dets[((size_t)b * p.max_per_img + k) * 5 + 4] > p.obj_thr) ++nobj;
     n_det[b] = nk;
-    n_obj[b] = nobj;
+    n_obj[b] = sh[45];
   }
 }
 
@@ -172,6 +175,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
 constexpr int kPairThreads = 256;
 constexpr int kPairChunk = 4 * kPairThreads;
 constexpr int kPairWords = MEHHUA_MAX_DETS / 32;
+constexpr size_t kPairSmem = MEHHUA_MAX_DETS * 16 + kPairChunk * 16 + kPairChunk * kPairWords * 4 + kPairChunk * 8;
 
 __global__ void __launch_bounds__(kPairThreads)
 k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes,
@@ -180,10 +184,12 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
                  const float* __restrict__ dets, const int* __restrict__ n_obj,
                  int* __restrict__ pair_row, int* __restrict__ pair_obj, int* __restrict__ pair_cls,
                  int* __restrict__ pair_off, float* __restrict__ lam_mean, unsigned* __restrict__ status) {
-  __shared__ float4 obox[MEHHUA_MAX_DETS];
-  __shared__ unsigned mask[kPairChunk * kPairWords];   // 32 KB
-  __shared__ int fg_idx[kPairChunk];
-  __shared__ int fg_cnt[kPairChunk];
+  extern __shared__ __align__(16) unsigned char k3b_smem[];
+  float4* obox = reinterpret_cast<float4*>(k3b_smem);                       // [MAX_DETS]
+  float4* fg_box = obox + MEHHUA_MAX_DETS;                                  // [kPairChunk]
+  unsigned* mask = reinterpret_cast<unsigned*>(fg_box + kPairChunk);        // [kPairChunk][kPairWords]
+  int* fg_idx = reinterpret_cast<int*>(mask + kPairChunk * kPairWords);     // [kPairChunk]
+  int* fg_cnt = fg_idx + kPairChunk;                                        // [kPairChunk]
   __shared__ int wsum[40];
   __shared__ int lvl_cnt[kMaxLevels];
   __shared__ int lvl_fg[kMaxLevels];
@@ -220,13 +226,13 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
         int pos = incl - nf;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (flags & (1 << j)) fg_idx[pos++] = r0 + j;
+          if (flags & (1 << j)) { fg_idx[pos] = r0 + j; fg_box[pos] = bx[r0 + j]; ++pos; }
       }
       __syncthreads();
       const int nfg = wsum[32];
       // (b) IoU masks: warp per foreground row, lane = object
       for (int e = w; e < nfg; e += kPairThreads / 32) {
-        const float4 rb = bx[fg_idx[e]];
+        const float4 rb = fg_box[e];
         const float area = __fmul_rn(__fsub_rn(rb.z, rb.x), __fsub_rn(rb.w, rb.y));
         int cnt = 0;
         for (int gq = 0; gq < nwords; ++gq) {

@@ -245,7 +245,12 @@ int launch_pairs(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, 
   if (!o || !o->boxes || !o->row_max || !o->row_argmax || !o->lam_rows || !o->level_fg || !o->dets || !o->n_obj ||
       !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->lam_mean)
     return arg_fail("null pair buffer");
-  k3b_pairs_kernel<<<p.B, kPairThreads, 0, st>>>(p, o->boxes, o->row_max, o->row_argmax, o->lam_rows, o->level_fg,
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k3b_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
+    attr = true;
+  }
+  k3b_pairs_kernel<<<p.B, kPairThreads, kPairSmem, st>>>(p, o->boxes, o->row_max, o->row_argmax, o->lam_rows, o->level_fg,
                                                  o->dets, o->n_obj, o->pair_row, o->pair_obj, o->pair_cls,
                                                  o->pair_off, o->lam_mean, ws.status);
   LAUNCHED("k3b_pairs_kernel");
