@@ -115,7 +115,7 @@ __device__ __forceinline__ void block_bitonic_desc(unsigned long long* buf, int 
   for (int size = 2; size <= n2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
-        const int lo = ((i / stride) * stride << 1) + (i % stride);
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));   // stride is a power of two
         const int hi = lo + stride;
         const bool desc = (lo & size) == 0;
         const unsigned long long a = buf[lo], b = buf[hi];

@@ -216,20 +216,26 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
             m = fmaxf(m, l2);
           }
         }
-        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with two cursors (even / odd
-        // list positions): each iteration one Philox block feeds one attempt per cursor, so a lane
-        // never idles while a neighbour retries and the two attempts overlap in the pipelines.
-        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall;
+        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with four cursors (list positions
+        // mod 4): each iteration two Philox blocks feed one attempt per cursor, so a lane never idles
+        // while a neighbour retries and the four attempts overlap in the pipelines.
+        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall, ic = active ? 2 : nsmall, id = active ? 3 : nsmall;
         unsigned kcall = 0;
         if (nsmall > 0) {
-          while (__any_sync(full, (ia < nsmall) | (ib < nsmall))) {
-            const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key);
-            unsigned ca, cb;
-            float la, lb;
+          while (__any_sync(full, (ia < nsmall) | (ib < nsmall) | (ic < nsmall) | (id < nsmall))) {
+            const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall, pid, gid), key);
+            const uint4 v = philox4x32_10(make_uint4((unsigned)t, kcall + 1u, pid, gid), key);
+            kcall += 2u;
+            unsigned ca, cb, cc, cd;
+            float la, lb, lc, ld;
             const bool oka = gs_attempt(ia, nsmall, w.x, w.y, a_small, a_cst4, ca, la);
             const bool okb = gs_attempt(ib, nsmall, w.z, w.w, a_small, a_cst4, cb, lb);
-            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), la); m = fmaxf(m, la); ia += 2; }
-            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), lb); m = fmaxf(m, lb); ib += 2; }
+            const bool okc = gs_attempt(ic, nsmall, v.x, v.y, a_small, a_cst4, cc, lc);
+            const bool okd = gs_attempt(id, nsmall, v.z, v.w, a_small, a_cst4, cd, ld);
+            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), la); m = fmaxf(m, la); ia += 4; }
+            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), lb); m = fmaxf(m, lb); ib += 4; }
+            if (okc) { sts_f32(a_lrow + cc * (kLStride * 4u), lc); m = fmaxf(m, lc); ic += 4; }
+            if (okd) { sts_f32(a_lrow + cd * (kLStride * 4u), ld); m = fmaxf(m, ld); id += 4; }
           }
         }
         __syncwarp();
