@@ -278,8 +278,13 @@ def main():
     k1a_s = stage_avg["k1a_keys"] * 1e-3
     achieved = k1a_bytes / k1a_s / 1e9 if k1a_s > 0 else 0.0
     k1_all_s = (stage_avg["k1a_keys"] + stage_avg["k1b_select"] + stage_avg["k1c_gather"]) * 1e-3
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1a_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(spec.name, {}).get(str(B))
     roofline = dict(bound="hbm", kernel="k1a_keys_kernel", achieved=achieved, peak=peak, unit="GB/s",
-                    frac=achieved / peak, traffic=None, peak_source=peak_src,
+                    frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=k1a_bytes,
                     k1_stage_achieved=B * spec.k1_bytes_per_image() / k1_all_s / 1e9 if k1_all_s > 0 else 0.0,
                     stage_ms_per_step=stage_avg)
