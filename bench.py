@@ -65,7 +65,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
