@@ -56,7 +56,7 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
 __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // per-warp shared memory, in floats:
-//   cst4[C] (float4: b*2^-32, 1/alpha, alpha-1, b) | lbuf[C*33] | alpha[C] | avg[C] | lists 3 x C bytes
+//   cst4[C] (float4: b, 1/alpha, alpha-1, -b) | lbuf[C*33] | alpha[C] | avg[C] | lists 3 x C bytes
 __host__ __device__ inline size_t k2_warp_floats(int C) {
   const size_t f = 4 * (size_t)C + (size_t)C * kLStride + 2 * (size_t)C + (3 * (size_t)C + 3) / 4;
   return (f + 3) & ~(size_t)3;
@@ -72,10 +72,14 @@ __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_wa
 __device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const unsigned w0, const unsigned w1,
                                            const unsigned s_small, const unsigned s_cst4, unsigned& c, float& l2) {
   c = lds_u8(s_small + min(i, nsmall - 1));
-  const float4 k = lds_v4(s_cst4 + c * 16u);            // b*2^-32, 1/alpha, alpha-1, b
-  const float pp = (float)w0 * k.x;
+  const float4 k = lds_v4(s_cst4 + c * 16u);            // b, 1/alpha, alpha-1, -b
+  // uniforms straight from the bits: f = 1.mantissa in [1,2), U = f - 1 (23-bit resolution), no
+  // int->float conversion on the SFU pipe
+  const float f0 = __uint_as_float(0x3f800000u | (w0 >> 9));
+  const float f1 = __uint_as_float(0x3f800000u | (w1 >> 9));
+  const float pp = fmaf(f0, k.x, k.w);                  // b * U1
   const bool lo = pp <= 1.f;
-  const float q = lo ? pp : (k.w - pp) * k.y;
+  const float q = lo ? pp : (k.x - pp) * k.y;
   const float lq = lg2_approx(q);
   const float l2a = lq * k.y;                           // log2 x, first branch
   const float rhsa = -kLog2e * ex2_approx(l2a);         // log2 exp(-x)
@@ -83,7 +87,8 @@ __device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const 
   const float rhsb = k.z * l2b;                         // log2 x^(alpha-1)
   l2 = lo ? l2a : l2b;
   const float rhs = lo ? rhsa : rhsb;
-  return (i < nsmall) & (lg2_approx((float)w1) - 32.f <= rhs);
+  // U2 = f1 - 1 + 2^-24 in (0,1): log2(U2) <= rhs
+  return (i < nsmall) & (lg2_approx(f1 - 0.99999994f) <= rhs);
 }
 
 __global__ void __launch_bounds__(kK2Threads)
@@ -158,7 +163,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       nbig += __popc(mb); nsmall += __popc(ms); nbad += __popc(mx);
       if (valid) {
         const float bb = fmaf(a, kInvE, 1.f);
-        cst4[c] = make_float4(bb * kTwoM32, bad ? 0.f : __fdiv_rn(1.f, a), a - 1.f, bb);
+        cst4[c] = make_float4(bb, bad ? 0.f : __fdiv_rn(1.f, a), a - 1.f, -bb);
         s_alpha[c] = bad ? 0.f : a;
         s_avg[c] = 0.f;
       }

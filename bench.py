@@ -206,8 +206,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     img_bytes = 4 * spec.num_priors * (spec.c_out + 5)
-    B = args.batch or max(1, min(64, int(2.2e9 // img_bytes)))        # ~2 GB of head outputs per step
-    ring = args.ring or max(2 * B, ((int(4.5e9 // img_bytes)) // B) * B)
+    B = args.batch or max(1, min(128, int(4.4e9 // img_bytes)))       # ~4.4 GB of head outputs per step
+    ring = args.ring or max(2 * B, ((int(9.0e9 // img_bytes)) // B) * B)
     ring = max(B, (ring // B) * B)
     pool_size = POOL_SIZES.get(spec.name, 100000)
     lo, hi = shard_range(pool_size, rank, world)
