@@ -18,6 +18,7 @@ ABI_VERSION = 1
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
 ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA = 1, 2, 4
+MODE_NMS, MODE_ALL = 0, 1
 
 
 class MehhuaError(RuntimeError):
@@ -38,7 +39,7 @@ class Config(C.Structure):
                 ("use_lambda", C.c_int32), ("n_samples", C.c_int32), ("agg_object", C.c_int32),
                 ("agg_scale", C.c_int32), ("agg_class", C.c_int32), ("cls_w", C.c_int32),
                 ("means", C.c_float * 4), ("stds", C.c_float * 4), ("wh_ratio_clip", C.c_float),
-                ("rescale", C.c_int32), ("pair_cap", C.c_int32), ("reserved", C.c_int32),
+                ("rescale", C.c_int32), ("pair_cap", C.c_int32), ("mode", C.c_int32),
                 ("seed", C.c_uint64)]
 
 
@@ -70,6 +71,8 @@ SYMBOLS = {
     "mehhua_k2_dirichlet_epi": (C.c_int, [_CFG, _LV, C.c_int32, _P, _P, _P, _BUF, _P, C.c_size_t, _P]),
     "mehhua_k3_hua": (C.c_int, [_CFG, _LV, C.c_int32, _BUF, _P, C.c_size_t, _P]),
     "mehhua_score_batch": (C.c_int, [_CFG, _LV, C.c_int32, _P, _P, _P, _BUF, _P, C.c_size_t, _P]),
+    "mehhua_all_fg_rows": (C.c_int, [_CFG, _LV, C.c_int32, _BUF, _P, C.c_size_t, _P]),
+    "mehhua_score_batch_all": (C.c_int, [_CFG, _LV, C.c_int32, _P, _BUF, _P, C.c_size_t, _P]),
     "mehhua_stage_timing_begin": (C.c_int, [C.c_int32]),
     "mehhua_stage_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mehhua_pool_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),

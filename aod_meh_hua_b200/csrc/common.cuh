@@ -34,6 +34,7 @@ struct Plan {
   int S, B, C, head, num_fg;
   int N;                // priors per image
   int K;                // rows per image (K_tot)
+  int row_stride;       // rows per image in score_rows / lam_rows (K; pair_cap in Entropy_ALL mode)
   int tiles_per_image;  // K1a tiles per image
   int nms_pre, max_per_img, pair_cap, n_samples;
   int use_lambda, agg_object, agg_scale, agg_class, cls_w, rescale;
@@ -51,6 +52,9 @@ struct Workspace {
   unsigned* cand_maxc;         // [B]      max candidate box coordinate, ordered-uint encoded
   unsigned* status;            // [1]
   int* work_counter;           // [4]      dynamic work queues
+  unsigned* fg_list;           // [B, pair_cap] Entropy_ALL: (level << 28 | prior) of every foreground prior
+  int* fg_cnt;                 // [B]
+  float* lam_part;             // [B, tiles_per_image] per-tile lambda sums (Entropy_ALL)
   size_t bytes;
 };
 
@@ -80,6 +84,14 @@ __device__ __forceinline__ int level_of_row(const Plan& p, int r) {
 #pragma unroll
   for (int i = 1; i < kMaxLevels; ++i)
     if (i < p.S && r >= p.lv[i].k_off) s = i;
+  return s;
+}
+
+// level that owns pair q of an image: pair_off[s] = first pair of level s (levels are contiguous)
+__device__ __forceinline__ int level_of_pair(const int* __restrict__ poff, int S, int q) {
+  int s = 0;
+  for (int i = 1; i < S; ++i)
+    if (q >= poff[i]) s = i;
   return s;
 }
 

@@ -138,13 +138,13 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
     const int b = lo, q = g - img_pref[b];
     const size_t pq = (size_t)b * p.pair_cap + q;
     const int row = pair_row[pq], obj = pair_obj[pq];
-    const int s = level_of_row(p, row);
+    const int s = level_of_pair(pair_off + b * (p.S + 1), p.S, q);
     float lamp = 1.f;
     if (p.use_lambda) {
-      const float lam = lam_rows[(size_t)b * p.K + row];
+      const float lam = lam_rows[(size_t)b * p.row_stride + row];
       lamp = __fmul_rn(__fdiv_rn(lam_mean[b * p.S + s], __fadd_rn(lam, p.lambda_eps)), p.lambda_scale);
     }
-    const float* srow = score_rows + ((size_t)b * p.K + row) * C;
+    const float* srow = score_rows + ((size_t)b * p.row_stride + row) * C;
     __syncwarp();
     // class lists: big (alpha >= 1), small (0 < alpha < 1), bad (alpha <= 0, denormal-tiny or non-finite)
     int nsmall = 0, nbig = 0, nbad = 0;

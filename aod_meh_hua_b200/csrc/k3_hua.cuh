@@ -343,7 +343,6 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int nobj = n_obj[b];
   const int np = pair_off[b * (p.S + 1) + p.S];
-  const int* prow = pair_row + (size_t)b * p.pair_cap;
   const int* pobj = pair_obj + (size_t)b * p.pair_cap;
   const int* pcls = pair_cls + (size_t)b * p.pair_cap;
   const float* punc = pair_unc + (size_t)b * p.pair_cap * 3;
@@ -361,7 +360,7 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
     for (int q = threadIdx.x; q < n2; q += kHuaThreads) {
       unsigned long long e = 0ull;
       if (q < np) {
-        const unsigned gk = (unsigned)((pobj[q] * p.S + level_of_row(p, prow[q])) * p.C + pcls[q]);
+        const unsigned gk = (unsigned)((pobj[q] * p.S + level_of_pair(pair_off + b * (p.S + 1), p.S, q)) * p.C + pcls[q]);
         e = ~(((unsigned long long)gk << 32) | (unsigned)q);
       }
       keys[q] = e;
@@ -441,7 +440,7 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
         if (pobj[q] != o) continue;                 // warp-uniform
         const int cls = pcls[q];
         if ((cls & 31) == lane) {
-          const int cell = level_of_row(p, prow[q]) * p.C + cls;
+          const int cell = level_of_pair(pair_off + b * (p.S + 1), p.S, q) * p.C + cls;
           ms[cell] += punc[q * 3 + 2];
           mc[cell] += 1;
         }

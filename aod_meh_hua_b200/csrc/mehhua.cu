@@ -13,6 +13,7 @@
 #include "k2_dirichlet.cuh"
 #include "k3_hua.cuh"
 #include "k4_pool_topk.cuh"
+#include "ka_entropy_all.cuh"
 
 using namespace mehhua;
 
@@ -66,6 +67,7 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   if (B < 1 || B > 1024) return arg_fail("batch must be 1..1024");
   if (cfg->pair_cap < 1) return arg_fail("pair_cap must be positive");
   if (cfg->n_samples < 1) return arg_fail("n_samples must be positive");
+  if (cfg->mode != MEHHUA_MODE_NMS && cfg->mode != MEHHUA_MODE_ALL) return arg_fail("mode");
   for (int a : {cfg->agg_object, cfg->agg_scale, cfg->agg_class})
     if (a < MEHHUA_AGG_SUM || a > MEHHUA_AGG_MAX) return arg_fail("aggregation op");
   Plan p;
@@ -76,7 +78,8 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   for (int s = 0; s < p.S; ++s) {
     LevelDev& L = p.lv[s];
     if (lv[s].H < 1 || lv[s].W < 1 || lv[s].A < 1) return arg_fail("level geometry");
-    if (need_ptrs && (!lv[s].logits || !lv[s].deltas || !lv[s].lambda || !lv[s].anchors))
+    if (need_ptrs && (!lv[s].logits || !lv[s].lambda)) return arg_fail("null level pointer");
+    if (need_ptrs && cfg->mode == MEHHUA_MODE_NMS && (!lv[s].deltas || !lv[s].anchors))
       return arg_fail("null level pointer");
     L.logits = lv[s].logits; L.deltas = lv[s].deltas; L.lam = lv[s].lambda; L.anchors = lv[s].anchors;
     L.H = lv[s].H; L.W = lv[s].W; L.A = lv[s].A; L.HW = L.H * L.W;
@@ -92,6 +95,10 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   }
   if (n_off > (1ll << 30) || k_off > (1 << 20) || tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
   p.N = (int)n_off; p.K = (int)k_off; p.tiles_per_image = (int)tile0;
+  p.row_stride = cfg->mode == MEHHUA_MODE_ALL ? cfg->pair_cap : p.K;
+  if (cfg->mode == MEHHUA_MODE_ALL)
+    for (int s = 0; s < p.S; ++s)
+      if (p.lv[s].n >= (1 << 28)) return arg_fail("level too large for Entropy_ALL");
   p.nms_pre = cfg->nms_pre; p.max_per_img = cfg->max_per_img; p.pair_cap = cfg->pair_cap;
   p.n_samples = cfg->n_samples; p.use_lambda = cfg->use_lambda;
   p.agg_object = cfg->agg_object; p.agg_scale = cfg->agg_scale; p.agg_class = cfg->agg_class;
@@ -116,6 +123,9 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   const size_t o_maxc = take((size_t)p.B * sizeof(unsigned));
   const size_t o_status = take(sizeof(unsigned));
   const size_t o_work = take(4 * sizeof(int));
+  const size_t o_fgl = take((size_t)p.B * p.pair_cap * sizeof(unsigned));
+  const size_t o_fgc = take((size_t)p.B * sizeof(int));
+  const size_t o_lamp = take((size_t)p.B * p.tiles_per_image * sizeof(float));
   if (ws) {
     char* b = static_cast<char*>(base);
     ws->keys = reinterpret_cast<float*>(b + o_keys);
@@ -124,6 +134,9 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
     ws->cand_maxc = reinterpret_cast<unsigned*>(b + o_maxc);
     ws->status = reinterpret_cast<unsigned*>(b + o_status);
     ws->work_counter = reinterpret_cast<int*>(b + o_work);
+    ws->fg_list = reinterpret_cast<unsigned*>(b + o_fgl);
+    ws->fg_cnt = reinterpret_cast<int*>(b + o_fgc);
+    ws->lam_part = reinterpret_cast<float*>(b + o_lamp);
     ws->bytes = off;
   }
   return off;
@@ -224,6 +237,41 @@ int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const
     case 21: return launch_k1_typed<21, MEHHUA_HEAD_SSD>(p, ws, img_shapes, scale_factors, o, st);
     case 81: return launch_k1_typed<81, MEHHUA_HEAD_SSD>(p, ws, img_shapes, scale_factors, o, st);
     default: return launch_k1_typed<0, MEHHUA_HEAD_SSD>(p, ws, img_shapes, scale_factors, o, st);
+  }
+}
+
+template <int C, int HEAD>
+int launch_all_typed(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
+  ka_fg_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(p, ws.fg_list, ws.fg_cnt, ws.lam_part, ws.status);
+  LAUNCHED("ka_fg_kernel");
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(ka_finalize_kernel<C, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAllSmem));
+    attr = true;
+  }
+  ka_finalize_kernel<C, HEAD><<<p.B, kAllThreads, kAllSmem, st>>>(
+      p, ws.fg_list, ws.fg_cnt, ws.lam_part, o->score_rows, o->lam_rows, o->topk_idx, o->row_max, o->row_argmax,
+      o->level_fg, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off, o->lam_mean, o->n_obj, o->n_det, ws.status);
+  LAUNCHED("ka_finalize_kernel");
+  return 0;
+}
+
+int launch_all(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!o || !o->score_rows || !o->lam_rows || !o->topk_idx || !o->row_max || !o->row_argmax || !o->level_fg ||
+      !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->lam_mean || !o->n_obj || !o->n_det)
+    return arg_fail("null Entropy_ALL buffer");
+  CU(cudaMemsetAsync(ws.fg_cnt, 0, (size_t)p.B * sizeof(int), st));
+  if (p.head == MEHHUA_HEAD_RETINA) {
+    switch (p.C) {
+      case 20: return launch_all_typed<20, MEHHUA_HEAD_RETINA>(p, ws, o, st);
+      case 80: return launch_all_typed<80, MEHHUA_HEAD_RETINA>(p, ws, o, st);
+      default: return launch_all_typed<0, MEHHUA_HEAD_RETINA>(p, ws, o, st);
+    }
+  }
+  switch (p.C) {
+    case 21: return launch_all_typed<21, MEHHUA_HEAD_SSD>(p, ws, o, st);
+    case 81: return launch_all_typed<81, MEHHUA_HEAD_SSD>(p, ws, o, st);
+    default: return launch_all_typed<0, MEHHUA_HEAD_SSD>(p, ws, o, st);
   }
 }
 
@@ -404,6 +452,27 @@ int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels,
   timer_mark(pr.stream, 7);
   if (g_timer.on && g_timer.calls < g_timer.max_calls) ++g_timer.calls;
   return rc;
+}
+
+int mehhua_all_fg_rows(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                       const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->mode != MEHHUA_MODE_ALL) return arg_fail("cfg->mode must be MEHHUA_MODE_ALL");
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  return launch_all(pr.plan, pr.ws, out, pr.stream);
+}
+
+int mehhua_score_batch_all(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                           const int64_t* image_ids, const mehhua_buffers_t* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->mode != MEHHUA_MODE_ALL) return arg_fail("cfg->mode must be MEHHUA_MODE_ALL");
+  Prepared pr;
+  int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
+  if (rc) return rc;
+  if ((rc = launch_all(pr.plan, pr.ws, out, pr.stream))) return rc;
+  if ((rc = launch_k2(pr.plan, pr.ws, image_ids, nullptr, nullptr, out, pr.stream))) return rc;
+  return launch_hua(pr.plan, out, pr.stream);
 }
 
 int mehhua_stage_timing_begin(int32_t max_calls) {

@@ -79,6 +79,10 @@ class B200ScoringMixin:
                     rescale=False, with_nms=True, **kwargs):
         scoring = bool(kwargs.get("isUnc")) and kwargs.get("uPool") == "Entropy_NMS" and with_nms \
             and "L_scores" in kwargs and not torch.onnx.is_in_onnx_export()
+        if bool(kwargs.get("isUnc")) and kwargs.get("uPool") == "Entropy_ALL" and not with_nms \
+                and "L_scores" in kwargs and (cfg is None or cfg is self.test_cfg):
+            return self._mehhua_entropy_all(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes,
+                                            scale_factors, **kwargs)
         if not scoring or (cfg is not None and cfg is not self.test_cfg):
             return super()._get_bboxes(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors,
                                        cfg, rescale, with_nms, **kwargs)
@@ -102,6 +106,38 @@ class B200ScoringMixin:
             maxconf = max_conf(mlvl_cls_scores, int(self.cls_out_channels))[0]
             return det_results, agged, maxconf
         return det_results, agged
+
+    def _mehhua_entropy_all(self, mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors,
+                            **kwargs):
+        """Entropy_ALL route (Lambda_L2.py:281-283, 362-365 -> ComputeScaleUnc + AggregateScaleUnc):
+        returns (det_results, AggedUnc).  The reference's det_results on this route are the raw
+        (boxes [N,4], scores [N,C+1]) of every prior, which no caller reads (apis/test.py:116 only
+        takes len()); they are returned here with zero rows."""
+        if kwargs.get("scaleUnc") or kwargs.get("saveMaxConf"):
+            raise NotImplementedError("scaleUnc / saveMaxConf outputs of the Entropy_ALL route")
+        B = mlvl_cls_scores[0].shape[0]
+        dev = mlvl_cls_scores[0].device
+        hw = tuple(int(v) for v in img_shapes[0][:2])
+        featmaps = [tuple(c.shape[-2:]) for c in mlvl_cls_scores]
+        c_out = int(self.cls_out_channels)
+        num_anchors = [c.shape[1] // c_out for c in mlvl_cls_scores]
+        key = ("all", tuple(featmaps), tuple(num_anchors), c_out, str(dev), kwargs["uPool2"], max(B, self.mehhua_max_batch))
+        cache = self.__dict__.setdefault("_mehhua_scorers", {})
+        if key not in cache:
+            spec = _spec_from_head(self, featmaps, num_anchors, hw)
+            p = self.mehhua_params
+            params = ScoringParams(n_samples=p.n_samples, fg_thr=p.fg_thr, lambda_scale=p.lambda_scale,
+                                   lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, agg=kwargs["uPool2"], seed=p.seed)
+            cache[key] = Scorer(spec, params, max_batch=max(B, self.mehhua_max_batch), device=dev, mode="all")
+        sc = cache[key]
+        ids = kwargs.get("image_ids")
+        if ids is None and "batchIdx" in kwargs:
+            ids = [int(kwargs["batchIdx"]) * B + j for j in range(B)]
+        res = sc.score(mlvl_cls_scores, mlvl_bbox_preds, kwargs["L_scores"], mlvl_anchors, img_shapes,
+                       scale_factors, image_ids=ids)
+        dets = [(torch.zeros(0, 4, device=dev), torch.zeros(0, c_out + (0 if getattr(self, "last_activation", "relu") == "softmax" else 1), device=dev))
+                for _ in range(B)]
+        return dets, [float(v) if v != 0 else 0 for v in res.image_scores.cpu().tolist()]
 
     # ------------------------------------------------------------------ narrowest boundary
     def ComputeObjUnc(self, mlvl_cls_scores, pos_bboxes, mlvl_scores, mlvl_Ls, mlvl_idces):

@@ -14,12 +14,14 @@ import numpy as np
 import torch
 
 from . import _lib
-from .specs import DetectorSpec, ScoringParams, parse_agg_spec
+from .specs import DetectorSpec, ScoringParams, parse_agg_spec, parse_scale_agg
 
 
-def make_config(spec: DetectorSpec, params: ScoringParams, pair_cap: int, rescale: bool = True) -> _lib.Config:
-    ao, asc, ac = parse_agg_spec(params.agg)
+def make_config(spec: DetectorSpec, params: ScoringParams, pair_cap: int, rescale: bool = True,
+                mode: str = "nms") -> _lib.Config:
+    ao, asc, ac = parse_scale_agg(params.agg) if mode == "all" else parse_agg_spec(params.agg)
     cfg = _lib.Config()
+    cfg.mode = _lib.MODE_ALL if mode == "all" else _lib.MODE_NMS
     cfg.head = spec.head
     cfg.c_out = spec.c_out
     cfg.num_levels = spec.num_levels
@@ -74,7 +76,10 @@ class Scorer:
     """Device-resident buffers + kernel launches for one detector geometry."""
 
     def __init__(self, spec: DetectorSpec, params: Optional[ScoringParams] = None, max_batch: int = 8,
-                 device="cuda:0", pair_cap: Optional[int] = None, rescale: bool = True):
+                 device="cuda:0", pair_cap: Optional[int] = None, rescale: bool = True, mode: str = "nms"):
+        """mode 'nms' = the Entropy_NMS route (objects from NMS, HUA over object/scale/class);
+        mode 'all' = the Entropy_ALL route (every foreground prior, params.agg is one of the four
+        'scaleX_classY' types, row buffers hold up to pair_cap foreground priors per image)."""
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MehhuaError("the MEH/HUA scoring path needs a CUDA device (sm_100a); none is visible")
@@ -82,15 +87,18 @@ class Scorer:
         self.params = params or ScoringParams()
         self.device = torch.device(device)
         self.max_batch = int(max_batch)
+        self.mode = mode
         K = spec.k_tot
         if pair_cap is None:
-            pair_cap = min(K * spec.max_per_img, 65536)
+            pair_cap = min(K * spec.max_per_img, 65536) if mode == "nms" else min(spec.num_priors, 16384)
         self.pair_cap = int(pair_cap)
-        self.cfg = make_config(spec, self.params, self.pair_cap, rescale)
+        self.cfg = make_config(spec, self.params, self.pair_cap, rescale, mode)
         self._shape_levels = _lib.LevelArray()
         for s, ((h, w), a) in enumerate(zip(spec.featmaps, spec.num_anchors)):
             self._shape_levels[s].H, self._shape_levels[s].W, self._shape_levels[s].A = h, w, a
         assert self.lib.mehhua_rows_per_image(C.byref(self.cfg), self._shape_levels) == K
+        if mode == "all":
+            K = self.pair_cap            # rows == pairs
         B, S, Cc, D, P = self.max_batch, spec.num_levels, spec.c_out, spec.max_per_img, self.pair_cap
         f32 = dict(dtype=torch.float32, device=self.device)
         i32 = dict(dtype=torch.int32, device=self.device)
@@ -217,9 +225,16 @@ class Scorer:
     def hua(self) -> None:
         _lib.check(self.lib.mehhua_k3_hua(*self._common(), C.byref(self.bufs), *self._ws()), "mehhua_k3_hua")
 
+    def all_rows(self) -> None:
+        _lib.check(self.lib.mehhua_all_fg_rows(*self._common(), C.byref(self.bufs), *self._ws()), "mehhua_all_fg_rows")
+
     def score_bound(self) -> None:
         """The whole path for the bound batch, one C call, no host sync."""
         ids = self._ids.data_ptr() if self._ids is not None else None
+        if self.mode == "all":
+            _lib.check(self.lib.mehhua_score_batch_all(*self._common(), ids, C.byref(self.bufs), *self._ws()),
+                       "mehhua_score_batch_all")
+            return
         _lib.check(self.lib.mehhua_score_batch(*self._common(), self._img_shapes.data_ptr(),
                                                self._scale_factors.data_ptr(), ids, C.byref(self.bufs),
                                                *self._ws()), "mehhua_score_batch")

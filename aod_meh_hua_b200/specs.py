@@ -40,6 +40,21 @@ def parse_agg_spec(spec: str) -> Tuple[int, int, int]:
     return found["object"], found["scale"], found["class"]
 
 
+_SCALE_TYPES = {"scaleAvg_classAvg": (AGG_AVG, AGG_AVG), "scaleSum_classSum": (AGG_SUM, AGG_SUM),
+                "scaleSum_classAvg": (AGG_SUM, AGG_AVG), "scaleAvg_classSum": (AGG_AVG, AGG_SUM)}
+
+
+def parse_scale_agg(kind: str) -> Tuple[int, int, int]:
+    """Entropy_ALL aggregation type -> (object_op, scale_op, class_op).  AggregateScaleUnc
+    (Lambda_L2.py:636-691) hard-codes exactly four types; there is a single pseudo-object, so the
+    object reducer is Sum.  (The reference silently returns an empty list for any other string,
+    which crashes its caller later; here it is a ValueError.)"""
+    if kind not in _SCALE_TYPES:
+        raise ValueError(f"unknown Entropy_ALL aggregation type {kind!r}; one of {sorted(_SCALE_TYPES)}")
+    sc, cl = _SCALE_TYPES[kind]
+    return AGG_SUM, sc, cl
+
+
 @dataclasses.dataclass(frozen=True)
 class DetectorSpec:
     """Geometry + constants of one detector configuration on the scoring path."""

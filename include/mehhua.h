@@ -53,6 +53,10 @@ extern "C" {
 #define MEHHUA_HEAD_RETINA 0   /* Lambda_L2Net: C_out = C, score = p / (sum(p) + 1e-20 + 1e-9) */
 #define MEHHUA_HEAD_SSD    1   /* MyLSSDHead:   C_out = C + 1 (background last), score = p     */
 
+#define MEHHUA_MODE_NMS 0      /* uncertainty_pool = 'Entropy_NMS' (Config_RetinaNet.py:14): objects from NMS */
+#define MEHHUA_MODE_ALL 1      /* uncertainty_pool = 'Entropy_ALL': every foreground prior, no objects;
+                                  rows == pairs, row buffers are [B, pair_cap, ...] */
+
 #define MEHHUA_AGG_SUM 0
 #define MEHHUA_AGG_AVG 1
 #define MEHHUA_AGG_MAX 2
@@ -89,7 +93,7 @@ typedef struct mehhua_config {
   float   wh_ratio_clip;   /* 16/1000 */
   int32_t rescale;         /* divide boxes by scale_factor (Lambda_L2.py:307-308) */
   int32_t pair_cap;        /* capacity of the per-image pair list */
-  int32_t reserved;
+  int32_t mode;            /* MEHHUA_MODE_*: which uncertainty_pool route the buffers are used for */
   uint64_t seed;           /* Philox key of the free-running sampler */
 } mehhua_config_t;
 
@@ -179,6 +183,20 @@ int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels,
                        const float* img_shapes, const float* scale_factors,
                        const int64_t* image_ids, const mehhua_buffers_t* out, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* Entropy_ALL route (cfg->mode = MEHHUA_MODE_ALL; replaces ComputeScaleUnc + AggregateScaleUnc,
+ * Lambda_L2.py:539-569, 636-691 and the nms_pre = -1 branch of _get_bboxes, :281-283).
+ * mehhua_all_fg_rows: stream the logits once, collect every prior with max foreground softmax >
+ * fg_thr, ordered by (level, prior index); writes for them score_rows (= softmax p) [B, pair_cap, C_out],
+ * lam_rows / topk_idx (= prior index) / row_max / row_argmax [B, pair_cap], level_fg, pair_* (rows ==
+ * pairs, object 0), pair_off, lam_mean (= mean lambda over ALL priors of the level), n_obj (0/1).
+ * mehhua_score_batch_all: that + K2 + K3c with agg_object = SUM, agg_scale / agg_class = the
+ * 'scaleX_classY' type; image_scores [B]. */
+int mehhua_all_fg_rows(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                       const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream);
+int mehhua_score_batch_all(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
+                           const int64_t* image_ids, const mehhua_buffers_t* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* Optional live timing of mehhua_score_batch's stages with CUDA events recorded on the call's own
  * stream (used by bench.py for the roofline numbers).  _begin arms it for up to max_calls calls;

@@ -39,6 +39,13 @@ CASES = [
 ]
 
 
+ALL_CASES = [
+    # name, spec, image ids, pool seed, sample seed, aggregation type
+    ("all_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 5, "scaleAvg_classAvg"),
+    ("all_ssd_voc", "tiny_ssd_voc", [0, 1, 2], 20, 5, "scaleSum_classAvg"),
+]
+
+
 def batch_checksum(batch) -> str:
     h = hashlib.sha256()
     for key in ("cls_scores", "bbox_preds", "L_scores", "anchors"):
@@ -106,6 +113,40 @@ def run_reference_case(spec_name, gids, pool_seed, sample_seed, sf, upool2, clsw
         k = int(np.argmin([a.shape[0] for a, _ in rec]))
         g["sample_block_index"] = np.int64(k)
         g["sample_block"] = rec[k][1].numpy()
+    return g
+
+
+def run_reference_all_case(spec_name, gids, pool_seed, sample_seed, kind):
+    """Entropy_ALL route of the reference's _get_bboxes (with_nms=False) -> ComputeScaleUnc ->
+    AggregateScaleUnc, all four aggregation types on the same draws."""
+    spec = get_spec(spec_name)
+    batch = SyntheticPool(spec, seed0=pool_seed).batch(gids)
+    head = RL.make_head("retina" if spec.head == HEAD_RETINA else "ssd", spec.c_out, spec.target_stds,
+                        spec.score_thr, spec.max_per_img, spec.nms_pre, spec.nms_iou)
+    g = dict(checksum=np.frombuffer(bytes.fromhex(batch_checksum(batch)), dtype=np.uint8))
+    captured = {}
+    real = head.ComputeScaleUnc
+
+    def spy(*a, **k):
+        captured["nested"] = real(*a, **k)
+        return captured["nested"]
+
+    head.ComputeScaleUnc = spy
+    for typ in ("scaleAvg_classAvg", "scaleSum_classSum", "scaleSum_classAvg", "scaleAvg_classSum"):
+        kw = dict(isUnc="Epistemic", uPool="Entropy_ALL", uPool2=typ, L_scores=batch["L_scores"], isEval=False,
+                  showNMS=False, saveUnc=False, saveMaxConf=False, clsW=False, scaleUnc=False, batchIdx=0)
+        torch.manual_seed(sample_seed)
+        dets, unc = head._get_bboxes(batch["cls_scores"], batch["bbox_preds"], batch["anchors"], batch["img_shapes"],
+                                     [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]], None, True,
+                                     False, **kw)
+        g[f"scores_{typ}"] = np.asarray(unc, dtype=np.float64)
+    groups = []
+    for b, img in enumerate(captured["nested"]):
+        for s, lvl in enumerate(img):
+            for c, (ale, epi) in lvl.items():
+                groups.append((b, s, int(c), float(ale), float(epi)))
+    g["groups"] = np.asarray(groups, dtype=np.float64).reshape(-1, 5)
+    g["det_shapes"] = np.asarray([list(d[0].shape) + list(d[1].shape) for d in dets], dtype=np.int64)
     return g
 
 
@@ -187,6 +228,11 @@ def main():
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")
+    for name, spec_name, gids, pseed, sseed, kind in ALL_CASES:
+        g = run_reference_all_case(spec_name, gids, pseed, sseed, kind)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **g)
+        print(f"{path}: {g['scores_' + kind]}, {os.path.getsize(path)} bytes")
     path = os.path.join(GOLDEN_DIR, "kats.npz")
     np.savez_compressed(path, **kat_goldens())
     print(path, os.path.getsize(path), "bytes")

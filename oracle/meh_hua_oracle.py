@@ -341,6 +341,68 @@ def aggregate_obj_scale_unc(nested, spec: str, cls_w: bool = False) -> List[floa
 
 
 # --------------------------------------------------------------------------------------------
+# stage a13: Entropy_ALL mode - ComputeScaleUnc + AggregateScaleUnc
+#                    (Lambda_L2.py:539-569, 636-691; My_L_ssd_head.py:484-515, 541-596)
+# --------------------------------------------------------------------------------------------
+def compute_scale_unc(cls_scores: List[torch.Tensor], L_scores: List[torch.Tensor], *, head: int, c_out: int,
+                      T: int = 500, fg_thr: float = 0.3, lambda_scale: float = 25.0, lambda_eps: float = 1e-7,
+                      sampler: SampleFn = default_sampler):
+    """Every prior with max softmax > fg_thr is sampled; no NMS / objects.  Returns (nested, flat):
+    nested[i][s][str(cls)] = (ale, epi) as the reference builds it."""
+    S = len(cls_scores)
+    B = cls_scores[0].shape[0]
+    nested = [[{} for _ in range(S)] for _ in range(B)]
+    flat = []
+    for s in range(S):
+        for i in range(B):
+            x = cls_scores[s][i].permute(1, 2, 0).reshape(-1, c_out)
+            p = x.softmax(dim=1)
+            conf = p.max(dim=1)[0] if head == HEAD_RETINA else p[:, :-1].max(dim=1)[0]
+            fg = conf > fg_thr
+            if not bool(fg.any()):
+                continue
+            lam = L_scores[s][i].permute(1, 2, 0).reshape(-1, 1)
+            lam_p = lam.mean() / (lam + lambda_eps) * lambda_scale
+            alpha = (p * lam_p)[fg]
+            smp = sampler(alpha, T, i, s)
+            total, ale, epi = uncertainty_from_samples(smp)
+            pcls = alpha.argmax(dim=1)
+            for c in pcls.unique():
+                m = pcls == c
+                nested[i][s][f"{c}"] = (ale[m].mean(), epi[m].mean())
+            flat.append(dict(image=i, level=s, prior=fg.nonzero()[:, 0].numpy(), cls=pcls.numpy(),
+                             alpha=alpha.numpy(), total=total.numpy(), ale=ale.numpy(), epi=epi.numpy()))
+    return nested, flat
+
+
+def aggregate_scale_unc(nested, kind: str):
+    """The four hard-coded aggregation types of AggregateScaleUnc (numpy float64 means / sums of the
+    group epistemic values); an unknown type yields an empty list, as in the reference."""
+    table = {"scaleAvg_classAvg": (np.mean, np.mean), "scaleSum_classSum": (np.sum, np.sum),
+             "scaleSum_classAvg": (np.sum, np.mean), "scaleAvg_classSum": (np.mean, np.sum)}
+    if kind not in table:
+        return []
+    f_scale, f_cls = table[kind]
+    out = []
+    for img in nested:
+        per_lvl = []
+        for lvl in img:
+            vals = [epi.item() for (_, (ale, epi)) in lvl.items()]
+            if vals:
+                per_lvl.append(f_cls(np.array(vals)))
+        out.append(f_scale(np.array(per_lvl)) if per_lvl else 0)
+    return out
+
+
+def score_batch_all(batch: Dict[str, object], *, head: int, c_out: int, T: int = 500, fg_thr: float = 0.3,
+                    lambda_scale: float = 25.0, lambda_eps: float = 1e-7, kind: str = "scaleAvg_classAvg",
+                    sampler: SampleFn = default_sampler, **_unused) -> Dict[str, object]:
+    nested, flat = compute_scale_unc(batch["cls_scores"], batch["L_scores"], head=head, c_out=c_out, T=T,
+                                     fg_thr=fg_thr, lambda_scale=lambda_scale, lambda_eps=lambda_eps, sampler=sampler)
+    return dict(nested=nested, flat=flat, image_scores=aggregate_scale_unc(nested, kind))
+
+
+# --------------------------------------------------------------------------------------------
 # the whole per-batch path (what _get_bboxes returns on the Entropy_NMS route)
 # --------------------------------------------------------------------------------------------
 def score_batch(batch: Dict[str, object], *, head: int, c_out: int, stds, nms_pre: int = 1000,

@@ -69,8 +69,18 @@ def test_get_bboxes_route(spec_name):
     np.testing.assert_allclose(unc, out["image_scores"], rtol=0.15, atol=0.05)
     # every other route falls through to the reference method
     assert head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, isUnc=None, isEval=True) == "reference-route"
-    kw2 = dict(KW, uPool="Entropy_ALL")
+    kw2 = dict(KW, uPool="Entropy_NoNMS")
     assert head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam, **kw2) == "reference-route"
+    # the Entropy_ALL route (with_nms=False, one of the four scale/class types) is taken over as well
+    torch.manual_seed(7)
+    want_all = O.score_batch_all(batch, kind="scaleSum_classAvg", **O.spec_kwargs(spec, ScoringParams()))["image_scores"]
+    kw3 = dict(KW, uPool="Entropy_ALL", uPool2="scaleSum_classAvg")
+    dets_all, unc_all = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam, **kw3)
+    assert len(dets_all) == 2 and len(unc_all) == 2
+    np.testing.assert_allclose(unc_all, np.asarray(want_all, dtype=np.float64), rtol=0.15, atol=0.03)
+    with pytest.raises(ValueError):
+        head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam,
+                         **dict(KW, uPool="Entropy_ALL", uPool2="objectSum_scaleMax_classSum"))
     with pytest.raises(KeyError):       # spec without an 'object' token, as ExtractAggFunc + AggregateObjScaleUnc
         head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, L_scores=lam,
                          **dict(KW, uPool2="scaleAvg_classAvg"))

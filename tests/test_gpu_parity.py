@@ -201,3 +201,52 @@ def test_sampler_moments_across_alpha_regimes():
                             params, seed_ids=(4, 1)).cpu().numpy().astype(np.float64)
     assert not np.array_equal(unc, unc2)
     np.testing.assert_allclose(unc2[:, 1], e_ent, rtol=5e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("spec_name,kind", [("tiny_retina_coco", "scaleAvg_classAvg"), ("tiny_ssd_voc", "scaleSum_classSum"),
+                                            ("tiny_retina_voc", "scaleSum_classAvg"), ("tiny_retina_coco", "scaleAvg_classSum")])
+def test_entropy_all_mode_parity(spec_name, kind):
+    """Entropy_ALL route (ComputeScaleUnc + AggregateScaleUnc): foreground prior lists, class keys,
+    alpha inputs, per-prior uncertainties under injection and image scores against the oracle."""
+    from oracle import meh_hua_oracle as O
+    from tests.helpers import Recorder
+    spec, batch = make_batch(spec_name, [0, 1, 2])
+    params = ScoringParams(agg=kind)
+    rec = Recorder(77)
+    out = O.score_batch_all(batch, kind=kind, sampler=rec, **O.spec_kwargs(spec, ScoringParams()))
+    sc = Scorer(spec, params, max_batch=3, device="cuda:0", mode="all")
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    sc.all_rows()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off)
+    sc.hua()
+    torch.cuda.synchronize()
+    assert sc.check_status() & 1 == 0
+    res = sc.result()
+    S = spec.num_levels
+    poff = res.pair_off.cpu().numpy()
+    for b in range(B):
+        recs = sorted([r for r in out["flat"] if r["image"] == b], key=lambda r: r["level"])
+        n = poff[b, S]
+        assert n == sum(len(r["prior"]) for r in recs)
+        for r in recs:
+            a, e = poff[b, r["level"]], poff[b, r["level"] + 1]
+            assert np.array_equal(res.topk_idx[b, a:e].cpu().numpy(), r["prior"])
+            assert np.array_equal(res.pair_cls[b, a:e].cpu().numpy(), r["cls"])
+            # alpha = p * lambda' with lambda' from the mean over ALL priors of the level
+            lam = res.lam_rows[b, a:e].cpu().numpy()
+            lam_p = res.lam_mean[b, r["level"]].item() / (lam + np.float32(1e-7)) * np.float32(25.0)
+            alpha = res.score_rows[b, a:e].cpu().numpy() * lam_p[:, None]
+            np.testing.assert_allclose(alpha, r["alpha"], rtol=2e-5, atol=1e-12)
+            unc = res.pair_unc[b, a:e].cpu().numpy()
+            np.testing.assert_allclose(unc[:, 0], r["total"], rtol=RTOL, atol=2e-6)
+            np.testing.assert_allclose(unc[:, 1], r["ale"], rtol=RTOL, atol=2e-6)
+            np.testing.assert_allclose(unc[:, 2], r["epi"], rtol=1e-4, atol=5e-6)
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float64),
+                               rtol=RTOL, atol=1e-5)
+    # free-running path end to end
+    res2 = sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                    batch["scale_factors"], image_ids=batch["gids"])
+    np.testing.assert_allclose(res2.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float64),
+                               rtol=0.2, atol=0.03)
