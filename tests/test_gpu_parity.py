@@ -250,3 +250,37 @@ def test_entropy_all_mode_parity(spec_name, kind):
                     batch["scale_factors"], image_ids=batch["gids"])
     np.testing.assert_allclose(res2.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float64),
                                rtol=0.2, atol=0.03)
+
+
+@pytest.mark.parametrize("spec_name,gid", [("cfg3_retina_r50_800x1344_coco", 7), ("cfg4_ssd512_coco", 3),
+                                           ("cfg1_retina_r50_512_voc", 5), ("cfg2_ssd300_voc", 11)])
+def test_full_size_configs_end_to_end(spec_name, gid):
+    """BASELINE.json shapes at full size (one image each, the oracle needs seconds): the whole path
+    with injected samples against the oracle, plus size-independent properties - descending top-k
+    keys, detections in descending score, idempotence, batch-composition independence."""
+    spec, batch, out, rec, res, st = _run(spec_name, [gid], (1.0, 1.0, 1.0, 1.0))
+    S = spec.num_levels
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float32),
+                               rtol=RTOL, atol=1e-5)
+    n = int(res.n_det[0])
+    assert n == len(out["dets"][0])
+    assert np.array_equal(res.det_flat[0, :n].cpu().numpy(), out["det_flat"][0].numpy())
+    d = res.dets[0, :n, 4].cpu().numpy()
+    assert np.all(d[:-1] >= d[1:])
+    koff = np.concatenate([[0], np.cumsum(spec.level_k)])
+    rm = res.row_max[0].cpu().numpy()
+    for s in range(S):
+        if spec.level_sizes[s] > spec.level_k[s] and spec.head == HEAD_RETINA:
+            k = rm[koff[s]:koff[s + 1]]                 # Retina: ranking key == row max, bit for bit
+            assert np.all(k[:-1] >= k[1:])
+    # free-running: same image scored alone and inside a batch of 3, twice -> bit-identical score
+    spec2, batch3 = make_batch(spec_name, [gid + 1, gid, gid + 2])
+    sc = Scorer(spec, ScoringParams(n_samples=100), max_batch=3, device="cuda:0")
+    r3 = sc.score(batch3["cls_scores"], batch3["bbox_preds"], batch3["L_scores"], batch3["anchors"],
+                  batch3["img_shapes"], batch3["scale_factors"], image_ids=batch3["gids"]).image_scores.cpu().numpy().copy()
+    r3b = sc.score(batch3["cls_scores"], batch3["bbox_preds"], batch3["L_scores"], batch3["anchors"],
+                   batch3["img_shapes"], batch3["scale_factors"], image_ids=batch3["gids"]).image_scores.cpu().numpy().copy()
+    r1 = sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                  batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"]).image_scores.cpu().numpy().copy()
+    assert np.array_equal(r3, r3b)
+    assert r1[0] == r3[1]
