@@ -309,11 +309,13 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
 // pairs are sorted by that key (bitonic sort in shared memory, pair ordinal as tie-break so every
 // group is summed in pair order - deterministic), run leaders produce the group means, and one
 // thread walks the sorted group table doing class -> level -> object aggregation with Sum / Avg /
-// Max selected per level of the hierarchy.  Images with more than kHuaCap pairs take a slower
-// path (one warp per object scanning the pair list) with the same arithmetic.
+// Max selected per level of the hierarchy.  The shared-memory sort holds kHuaCap pairs; an image
+// with more pairs is processed in several rounds over ascending object ranges (each range's pairs
+// fit; one object never has more pairs than there are rows), the walk carrying the object-level
+// accumulator across rounds.
 // ------------------------------------------------------------------------------------------
 constexpr int kHuaThreads = 256;
-constexpr int kHuaCap = 4096;
+constexpr int kHuaCap = 8192;
 
 __device__ __forceinline__ float agg_combine(int op, float acc, float v) {
   return op == MEHHUA_AGG_MAX ? fmaxf(acc, v) : acc + v;
@@ -323,57 +325,81 @@ __device__ __forceinline__ float agg_finish(int op, float acc, int n) {
 }
 
 __host__ __device__ inline size_t k3c_smem_bytes(int S, int C) {
-  const size_t fast = (size_t)kHuaCap * 8 + (size_t)kHuaCap * 8;                 // sort keys + group (key, mean)
-  const size_t slow = (size_t)(kHuaThreads / 32) * S * C * 8 + MEHHUA_MAX_DETS * 8;
-  return (fast > slow ? fast : slow) + ((C + 31) / 32) * 4 + 64 * 4;
+  (void)S;
+  return (size_t)kHuaCap * 16 + (MEHHUA_MAX_DETS + 1) * 4 + ((C + 31) / 32) * 4 + 64 * 4;
 }
 
 __global__ void __launch_bounds__(kHuaThreads)
 k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
                const int* __restrict__ pair_obj, const int* __restrict__ pair_cls,
                const int* __restrict__ pair_off, const float* __restrict__ pair_unc,
-               const int* __restrict__ n_obj, float* __restrict__ image_scores) {
+               const int* __restrict__ n_obj, float* __restrict__ image_scores, unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k3c_smem[];
-  const size_t fast = (size_t)kHuaCap * 16;
-  const size_t slow = (size_t)(kHuaThreads / 32) * p.S * p.C * 8 + MEHHUA_MAX_DETS * 8;
-  unsigned* cls_seen = reinterpret_cast<unsigned*>(k3c_smem + (fast > slow ? fast : slow));   // [(C+31)/32]
-  int* sh = reinterpret_cast<int*>(cls_seen + (p.C + 31) / 32);                               // 64 ints
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(k3c_smem);           // [kHuaCap]
+  unsigned* gkey = reinterpret_cast<unsigned*>(keys + kHuaCap);                          // [kHuaCap]
+  float* gval = reinterpret_cast<float*>(gkey + kHuaCap);                                // [kHuaCap]
+  int* ocnt = reinterpret_cast<int*>(gval + kHuaCap);                                    // [MAX_DETS + 1]
+  unsigned* cls_seen = reinterpret_cast<unsigned*>(ocnt + MEHHUA_MAX_DETS + 1);          // [(C+31)/32]
+  int* sh = reinterpret_cast<int*>(cls_seen + (p.C + 31) / 32);                          // 64 ints
 
   const int b = blockIdx.x;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nobj = n_obj[b];
+  const int nobj = min(n_obj[b], MEHHUA_MAX_DETS);
   const int np = pair_off[b * (p.S + 1) + p.S];
   const int* pobj = pair_obj + (size_t)b * p.pair_cap;
   const int* pcls = pair_cls + (size_t)b * p.pair_cap;
   const float* punc = pair_unc + (size_t)b * p.pair_cap * 3;
+  const int* poff = pair_off + b * (p.S + 1);
   for (int i = threadIdx.x; i < (p.C + 31) / 32; i += kHuaThreads) cls_seen[i] = 0u;
+  for (int i = threadIdx.x; i <= MEHHUA_MAX_DETS; i += kHuaThreads) ocnt[i] = 0;
   __syncthreads();
-  float out = 0.f;
-
-  if (np <= kHuaCap) {
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(k3c_smem);           // [kHuaCap]
-    unsigned* gkey = reinterpret_cast<unsigned*>(keys + kHuaCap);                          // [kHuaCap]
-    float* gval = reinterpret_cast<float*>(gkey + kHuaCap);                                // [kHuaCap]
-    int n2 = 1;
-    while (n2 < np) n2 <<= 1;
-    // inverted composite so the descending sort yields ascending (group key, pair ordinal)
-    for (int q = threadIdx.x; q < n2; q += kHuaThreads) {
-      unsigned long long e = 0ull;
-      if (q < np) {
-        const unsigned gk = (unsigned)((pobj[q] * p.S + level_of_pair(pair_off + b * (p.S + 1), p.S, q)) * p.C + pcls[q]);
-        e = ~(((unsigned long long)gk << 32) | (unsigned)q);
+  if (np > kHuaCap) {   // pairs per object, needed to cut the object axis into ranges that fit
+    for (int q = threadIdx.x; q < np; q += kHuaThreads) atomicAdd(&ocnt[min(pobj[q], MEHHUA_MAX_DETS)], 1);
+    __syncthreads();
+  }
+  // object-level accumulator of the walk (thread 0 only)
+  float oacc = 0.f;
+  int on = 0;
+  int o_lo = 0;
+  while (o_lo < max(nobj, 1)) {
+    // range [o_lo, o_hi): everything when the image fits, else as many whole objects as fit
+    int o_hi = max(nobj, 1);
+    if (np > kHuaCap) {
+      if (threadIdx.x == 0) {
+        int acc = 0, o = o_lo;
+        while (o < nobj && acc + ocnt[o] <= kHuaCap) { acc += ocnt[o]; ++o; }
+        if (o == o_lo) { atomicOr(status, MEHHUA_ST_PAIR_OVERFLOW); ++o; }   // one object alone overflows the sort
+        sh[41] = o;
       }
-      keys[q] = e;
+      __syncthreads();
+      o_hi = sh[41];
     }
+    if (threadIdx.x == 0) sh[42] = 0;
+    __syncthreads();
+    // collect the range's pairs as inverted composites (descending sort -> ascending (key, ordinal))
+    for (int q = threadIdx.x; q < np; q += kHuaThreads) {
+      const int o = pobj[q];
+      if (o >= o_lo && o < o_hi) {
+        const int pos = atomicAdd(&sh[42], 1);
+        if (pos < kHuaCap) {
+          const unsigned gk = (unsigned)((o * p.S + level_of_pair(poff, p.S, q)) * p.C + pcls[q]);
+          keys[pos] = ~(((unsigned long long)gk << 32) | (unsigned)q);
+        }
+      }
+    }
+    __syncthreads();
+    const int m = min(sh[42], kHuaCap);
+    int n2 = 1;
+    while (n2 < m) n2 <<= 1;
+    for (int i = m + threadIdx.x; i < n2; i += kHuaThreads) keys[i] = 0ull;
     __syncthreads();
     block_bitonic_desc<kHuaThreads>(keys, n2);
     // run leaders -> group means, written in key order
     int running = 0;
-    for (int base = 0; base < np; base += kHuaThreads) {
+    for (int base = 0; base < m; base += kHuaThreads) {
       const int i = base + threadIdx.x;
       unsigned gk = 0u;
       bool leader = false;
-      if (i < np) {
+      if (i < m) {
         gk = (unsigned)((~keys[i]) >> 32);
         leader = (i == 0) || gk != (unsigned)((~keys[i - 1]) >> 32);
       }
@@ -382,7 +408,7 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
       if (leader) {
         float sum = 0.f;
         int cnt = 0;
-        for (int j = i; j < np; ++j) {
+        for (int j = i; j < m; ++j) {
           const unsigned long long e = ~keys[j];
           if ((unsigned)(e >> 32) != gk) break;
           sum += punc[(unsigned)(e & 0xffffffffull) * 3 + 2];     // epistemic, in pair order
@@ -398,11 +424,9 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
       running += sh[40];
       __syncthreads();
     }
-    // one thread walks the (object, level, class)-sorted group table
+    // one thread walks the (object, level, class)-sorted group table of the range
     if (threadIdx.x == 0) {
       const int ng = running;
-      float oacc = 0.f;
-      int on = 0;
       int g = 0;
       while (g < ng) {
         const unsigned obj = gkey[g] / (unsigned)(p.S * p.C);
@@ -421,66 +445,12 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
         oacc = (on == 0) ? lv : agg_combine(p.agg_object, oacc, lv);
         ++on;
       }
-      out = on > 0 ? agg_finish(p.agg_object, oacc, on) : 0.f;
-    }
-  } else {
-    const int cells = p.S * p.C;
-    float* csum = reinterpret_cast<float*>(k3c_smem);                 // [warps][cells]
-    int* ccnt = reinterpret_cast<int*>(csum + (kHuaThreads / 32) * cells);
-    float* oval = reinterpret_cast<float*>(ccnt + (kHuaThreads / 32) * cells);   // [MAX_DETS]
-    int* ohas = reinterpret_cast<int*>(oval + MEHHUA_MAX_DETS);                   // [MAX_DETS]
-    for (int i = threadIdx.x; i < MEHHUA_MAX_DETS; i += kHuaThreads) { oval[i] = 0.f; ohas[i] = 0; }
-    __syncthreads();
-    float* ms = csum + w * cells;
-    int* mc = ccnt + w * cells;
-    for (int o = w; o < nobj; o += kHuaThreads / 32) {
-      for (int i = lane; i < cells; i += 32) { ms[i] = 0.f; mc[i] = 0; }
-      __syncwarp();
-      for (int q = 0; q < np; ++q) {
-        if (pobj[q] != o) continue;                 // warp-uniform
-        const int cls = pcls[q];
-        if ((cls & 31) == lane) {
-          const int cell = level_of_pair(pair_off + b * (p.S + 1), p.S, q) * p.C + cls;
-          ms[cell] += punc[q * 3 + 2];
-          mc[cell] += 1;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {       // sequential class -> level aggregation, same order as the fast path
-        float lacc = 0.f;
-        int ln = 0;
-        for (int s = 0; s < p.S; ++s) {
-          float cacc = (p.agg_class == MEHHUA_AGG_MAX) ? -FLT_MAX : 0.f;
-          int cn = 0;
-          for (int c = 0; c < p.C; ++c) {
-            const int k = mc[s * p.C + c];
-            if (k > 0) {
-              cacc = agg_combine(p.agg_class, cacc, __fdiv_rn(ms[s * p.C + c], (float)k));
-              ++cn;
-              atomicOr(&cls_seen[c >> 5], 1u << (c & 31));
-            }
-          }
-          if (cn > 0) {
-            const float cv = agg_finish(p.agg_class, cacc, cn);
-            lacc = (ln == 0) ? cv : agg_combine(p.agg_scale, lacc, cv);
-            ++ln;
-          }
-        }
-        if (ln > 0) { oval[o] = agg_finish(p.agg_scale, lacc, ln); ohas[o] = 1; }
-      }
-      __syncwarp();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float acc = 0.f;
-      int n = 0;
-      for (int o = 0; o < nobj; ++o)
-        if (ohas[o]) { acc = (n == 0) ? oval[o] : agg_combine(p.agg_object, acc, oval[o]); ++n; }
-      out = n > 0 ? agg_finish(p.agg_object, acc, n) : 0.f;
-    }
+    o_lo = o_hi;
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
+    float out = on > 0 ? agg_finish(p.agg_object, oacc, on) : 0.f;
     if (p.cls_w) {
       int k = 0;
       for (int i = 0; i < (p.C + 31) / 32; ++i) k += __popc(cls_seen[i]);

@@ -330,7 +330,7 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
   return 0;
 }
 
-int launch_hua(const Plan& p, const mehhua_buffers_t* o, cudaStream_t st) {
+int launch_hua(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
   if (!o || !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->pair_unc || !o->n_obj ||
       !o->image_scores)
     return arg_fail("null HUA buffer");
@@ -342,7 +342,7 @@ int launch_hua(const Plan& p, const mehhua_buffers_t* o, cudaStream_t st) {
     attr = smem;
   }
   k3c_hua_kernel<<<p.B, kHuaThreads, smem, st>>>(p, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off,
-                                                o->pair_unc, o->n_obj, o->image_scores);
+                                                o->pair_unc, o->n_obj, o->image_scores, ws.status);
   LAUNCHED("k3c_hua_kernel");
   return 0;
 }
@@ -431,7 +431,7 @@ int mehhua_k3_hua(const mehhua_config_t* cfg, const mehhua_level_t* levels, int3
   Prepared pr;
   int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
   if (rc) return rc;
-  return launch_hua(pr.plan, out, pr.stream);
+  return launch_hua(pr.plan, pr.ws, out, pr.stream);
 }
 
 int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
@@ -448,7 +448,7 @@ int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels,
   timer_mark(pr.stream, 5);
   if ((rc = launch_k2(pr.plan, pr.ws, image_ids, nullptr, nullptr, out, pr.stream))) return rc;
   timer_mark(pr.stream, 6);
-  rc = launch_hua(pr.plan, out, pr.stream);
+  rc = launch_hua(pr.plan, pr.ws, out, pr.stream);
   timer_mark(pr.stream, 7);
   if (g_timer.on && g_timer.calls < g_timer.max_calls) ++g_timer.calls;
   return rc;
@@ -472,7 +472,7 @@ int mehhua_score_batch_all(const mehhua_config_t* cfg, const mehhua_level_t* lev
   if (rc) return rc;
   if ((rc = launch_all(pr.plan, pr.ws, out, pr.stream))) return rc;
   if ((rc = launch_k2(pr.plan, pr.ws, image_ids, nullptr, nullptr, out, pr.stream))) return rc;
-  return launch_hua(pr.plan, out, pr.stream);
+  return launch_hua(pr.plan, pr.ws, out, pr.stream);
 }
 
 int mehhua_stage_timing_begin(int32_t max_calls) {

@@ -206,16 +206,16 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     img_bytes = 4 * spec.num_priors * (spec.c_out + 5)
-    B = args.batch or max(1, min(128, int(4.4e9 // img_bytes)))       # ~4.4 GB of head outputs per step
-    ring = args.ring or max(2 * B, ((int(9.0e9 // img_bytes)) // B) * B)
-    ring = max(B, (ring // B) * B)
+    B = args.batch or max(1, min(128, int(8.8e9 // img_bytes)))       # <= 8.8 GB of head outputs per step
+    ring = args.ring or max(2 * B, ((int(17.6e9 // img_bytes)) // B) * B)
+    ring = max(B, (min(ring, 8 * B) // B) * B)
     pool_size = POOL_SIZES.get(spec.name, 100000)
     lo, hi = shard_range(pool_size, rank, world)
     synth, cls, reg, lam = build_ring(spec, ring, lo, device)
     sc = Scorer(spec, params, max_batch=B, device=device)
     shp = torch.tensor([[spec.img_hw[0], spec.img_hw[1]]] * B, dtype=torch.float32, device=device)
     sf = torch.ones(B, 4, device=device)
-    pool_scores = torch.zeros(hi - lo, device=device)
+    pool_scores = torch.zeros(max(hi - lo, B), device=device)
     n_slots = ring // B
     slot_ptrs = []
     for j in range(n_slots):
@@ -233,7 +233,7 @@ def main():
         pool_scores[dst:dst + B].copy_(sc.t["image_scores"][:B], non_blocking=True)
 
     def finish():
-        allsc = gather_scores(pool_scores, pool_size, rank, world) if world > 1 else pool_scores
+        allsc = gather_scores(pool_scores[:n_local], pool_size, rank, world) if world > 1 else pool_scores
         k = max(1, min(int(0.025 * pool_size), allsc.numel()))
         return pool_topk(allsc, k)
 

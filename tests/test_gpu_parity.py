@@ -284,3 +284,20 @@ def test_full_size_configs_end_to_end(spec_name, gid):
                   batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"]).image_scores.cpu().numpy().copy()
     assert np.array_equal(r3, r3b)
     assert r1[0] == r3[1]
+
+
+def test_many_pairs_take_the_object_range_rounds():
+    """Lowered fg / cluster thresholds give ~26 000 (box, object) pairs for one image - more than the
+    K3c shared-memory sort holds (8192), so the object-range rounds are exercised; samples injected,
+    T reduced to keep the oracle light.  Also covers non-default thresholds on every stage."""
+    params = ScoringParams(n_samples=4, fg_thr=0.1, cluster_iou=0.2)
+    spec, batch, out, rec, res, st = _run("tiny_retina_voc", [0], (1.0, 1.0, 1.0, 1.0), params)
+    n_pairs = int(res.pair_off[0, spec.num_levels])
+    assert n_pairs == sum(len(r["row"]) for r in out["flat"])
+    assert n_pairs > 8192, n_pairs
+    row, obj, cls, tot, ale, epi, recs = oracle_pairs(out, 0)
+    assert np.array_equal(res.pair_row[0, :n_pairs].cpu().numpy(), row)
+    assert np.array_equal(res.pair_obj[0, :n_pairs].cpu().numpy(), obj)
+    np.testing.assert_allclose(res.pair_unc[0, :n_pairs, 2].cpu().numpy(), epi, rtol=1e-4, atol=5e-6)
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float32),
+                               rtol=RTOL, atol=1e-4)
