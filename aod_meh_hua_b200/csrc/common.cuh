@@ -25,6 +25,8 @@ struct LevelDev {
   int tpp;    // K1a tiles per (image, anchor) plane
   int tile0;  // first K1a tile of the level inside one image's tile list
   int topk;   // 1 when n > k (the per-level top-k is active)
+  int rescan; // 1 when the level's rows are produced by the coalesced rescan kernel (no top-k, or k >= n/8)
+  int rtile0; // first rescan tile of the level inside one image's rescan tile list
   int pad;
 };
 
@@ -36,6 +38,7 @@ struct Plan {
   int K;                // rows per image (K_tot)
   int row_stride;       // rows per image in score_rows / lam_rows (K; pair_cap in Entropy_ALL mode)
   int tiles_per_image;  // K1a tiles per image
+  int rtiles_per_image; // K1c rescan tiles per image
   int nms_pre, max_per_img, pair_cap, n_samples;
   int use_lambda, agg_object, agg_scale, agg_class, cls_w, rescale;
   float score_thr, nms_iou, fg_thr, obj_thr, cluster_iou, lambda_scale, lambda_eps;
@@ -52,6 +55,7 @@ struct Workspace {
   unsigned* cand_maxc;         // [B]      max candidate box coordinate, ordered-uint encoded
   unsigned* status;            // [1]
   int* work_counter;           // [4]      dynamic work queues
+  int* inv_map;                // [B, N]   position -> row of the dense top-k levels (-1 = not kept)
   unsigned* fg_list;           // [B, pair_cap] Entropy_ALL: (level << 28 | prior) of every foreground prior
   int* fg_cnt;                 // [B]
   float* lam_part;             // [B, tiles_per_image] per-tile lambda sums (Entropy_ALL)

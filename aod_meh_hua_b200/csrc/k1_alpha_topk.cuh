@@ -117,7 +117,7 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSelThreads)
 k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys,
-                  int* __restrict__ topk_idx, unsigned* __restrict__ status) {
+                  int* __restrict__ topk_idx, int* __restrict__ inv_map, unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k1b_smem[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(k1b_smem);   // kSelCap
   int* hist = reinterpret_cast<int*>(buf + kSelCap);                            // 4096
@@ -137,10 +137,16 @@ k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys
   const int cnt = block_collect_topk<kSelThreads, kSelCap, 0>(get, L.n, L.k, ~0ull, buf, hist, sh, status);
   int* out = topk_idx + (size_t)b * p.K + L.k_off;
   const int k = min(L.k, cnt);
+  int* inv = inv_map + (size_t)b * p.N + L.n_off;
+  if (L.rescan) {       // dense level: the rescan kernel finds rows through the inverse map
+    for (int j = threadIdx.x; j < L.n; j += kSelThreads) inv[j] = -1;
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < k; i += kSelThreads) {
     const int j = (int)(0xffffffffu - (unsigned)(buf[i] & 0xffffffffull));
     const int a = j / L.HW;
     out[i] = (j - a * L.HW) * L.A + a;
+    if (L.rescan) inv[j] = L.k_off + i;
   }
 }
 
@@ -149,42 +155,36 @@ k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys
 // lambda, decoded box, row max / argmax and append its NMS candidates (score > score_thr).
 // grid = (ceil(K / 128), B).
 // ------------------------------------------------------------------------------------------
+// The C logits of prior (b, a, hw) of level L into registers (stride H*W between classes).
+template <int C>
+__device__ __forceinline__ void k1_load_logits(const LevelDev& L, const int b, const int a, const int hw,
+                                               float (&x)[C > 0 ? C : 1]) {
+  if constexpr (C > 0) {
+    const float* __restrict__ src = L.logits + ((size_t)(b * L.A + a) * C) * L.HW + hw;
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = __ldg(src + (size_t)c * L.HW);
+  }
+}
+
+// What K1c produces for one kept row r = prior n of level L (used by the gather and rescan kernels):
+// softmax row (bit-identical to K1a's arithmetic), score row, lambda, decoded box, row max /
+// argmax, and the number of NMS candidates of the row.
 template <int C, int HEAD>
-__global__ void __launch_bounds__(kGatherThreads)
-k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
-                  const float* __restrict__ scale_factors, int* __restrict__ topk_idx,
-                  float* __restrict__ score_rows, float* __restrict__ lam_rows,
-                  float* __restrict__ boxes, float* __restrict__ row_max, int* __restrict__ row_argmax,
-                  unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
-                  unsigned* __restrict__ cand_maxc) {
-  const int b = blockIdx.y;
-  const int r = blockIdx.x * kGatherThreads + threadIdx.x;
-  const bool live = r < p.K;
+__device__ __forceinline__ void k1_row_body(const Plan& p, const LevelDev& L, const int b, const int r, const int n,
+                                            const float* __restrict__ img_shapes, const float* __restrict__ scale_factors,
+                                            float* __restrict__ score_rows, float* __restrict__ lam_rows,
+                                            float* __restrict__ boxes, float* __restrict__ row_max,
+                                            int* __restrict__ row_argmax, float (&x)[C > 0 ? C : 1],
+                                            float* tile_row, int& ncand, float& bmax, float*& srow) {
   const int CC = (C > 0) ? C : p.C;
   const int NF = p.num_fg;
-  int ncand = 0;
-  float bmax = 0.f;
-  float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* srow = nullptr;
-  if (live) {
-    const int s = level_of_row(p, r);
-    const LevelDev& L = p.lv[s];
-    int n;
-    if (L.topk) {
-      n = topk_idx[(size_t)b * p.K + r];
-    } else {
-      n = r - L.k_off;
-      topk_idx[(size_t)b * p.K + r] = n;
-    }
+  float4 box;
     const int hw = n / L.A, a = n - hw * L.A;
     const float* __restrict__ src = L.logits + ((size_t)(b * L.A + a) * CC) * L.HW + hw;
     srow = score_rows + ((size_t)b * p.K + r) * CC;
     float best = -1.f;
     int arg = 0;
-    if constexpr (C > 0) {
-      float x[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) x[c] = __ldg(src + (size_t)c * L.HW);
+    if constexpr (C > 0) {      // x[] holds the row's logits, loaded by the caller
       float inv, den, pfg;
       softmax_regs<C, HEAD>(x, inv, den, pfg);
 #pragma unroll
@@ -196,7 +196,7 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
         if (c < NF && sc > p.score_thr) ++ncand;
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) srow[c] = x[c];
+      for (int c = 0; c < C; ++c) tile_row[c] = x[c];     // staged in shared memory, flushed coalesced
     } else {
       float m, inv, den, pfg;
       softmax_stream<HEAD>(src, (size_t)L.HW, CC, m, inv, den, pfg);
@@ -205,7 +205,7 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
         const float e = ex2_approx(fmaf(__ldg(src + (size_t)c * L.HW), kLog2e, nml2));
         const float pc = __fmul_rn(e, inv);
         const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
-        srow[c] = sc;
+        tile_row[c] = sc;
         if (sc > best) { best = sc; arg = c; }
         if (c < NF && sc > p.score_thr) ++ncand;
       }
@@ -250,8 +250,14 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
     }
     reinterpret_cast<float4*>(boxes)[(size_t)b * p.K + r] = box;
     bmax = fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w));
-  }
-  // warp-aggregated append of this row's candidates (one atomic per warp)
+}
+
+// warp-aggregated append of each lane's NMS candidates (score > score_thr): one atomic per warp
+__device__ __forceinline__ void k1_append_candidates(const Plan& p, const int b, const int r, const int ncand,
+                                                     const float bmax, const float* srow /* this lane's scores */,
+                                                     unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
+                                                     unsigned* __restrict__ cand_maxc) {
+  const int NF = p.num_fg;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int incl = ncand;
@@ -278,6 +284,114 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
                  (unsigned long long)(0xffffffffu - (unsigned)(r * NF + c));
     }
   }
+}
+
+// Row staging: a lane's C scores go to its row of a shared-memory tile (odd stride: conflict-free),
+// then the warp writes the 32 rows out with coalesced stores (3 instructions per 80-float row
+// instead of 80 instructions x 32 scattered sectors).
+template <int C> struct K1Tile { static constexpr int stride = (C % 2 == 0) ? C + 1 : C + 2; };
+
+template <int C>
+__device__ __forceinline__ void k1_flush_rows(const float* tile /* warp's [32][stride] */, float* srow) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long mine = reinterpret_cast<unsigned long long>(srow);
+  __syncwarp();
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const unsigned long long d = __shfl_sync(full, mine, i);
+    if (d == 0ull) continue;                       // warp-uniform: lane i has no row
+    float* dst = reinterpret_cast<float*>(d);
+    const float* src = tile + i * K1Tile<C>::stride;
+    for (int c = lane; c < C; c += 32) dst[c] = src[c];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c (gather form): one thread per kept row of the SPARSE top-k levels (k << N): re-reads the
+// row's C logits with stride H*W (sector-granular traffic, 8*k*C*4 bytes per level).
+// grid = (ceil(K / 128), B); rows of dense / direct levels are left to the rescan kernel.
+// ------------------------------------------------------------------------------------------
+template <int C, int HEAD>
+__global__ void __launch_bounds__(kGatherThreads)
+k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
+                  const float* __restrict__ scale_factors, const int* __restrict__ topk_idx,
+                  float* __restrict__ score_rows, float* __restrict__ lam_rows,
+                  float* __restrict__ boxes, float* __restrict__ row_max, int* __restrict__ row_argmax,
+                  unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
+                  unsigned* __restrict__ cand_maxc) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * kGatherThreads + threadIdx.x;
+  int ncand = 0;
+  float bmax = 0.f;
+  float* srow = nullptr;
+  __shared__ float tile[(C > 0) ? (kGatherThreads * K1Tile<C>::stride) : 1];
+  float* tile_row = (C > 0) ? tile + threadIdx.x * K1Tile<C>::stride : nullptr;
+  if (r < p.K) {
+    const LevelDev& L = p.lv[level_of_row(p, r)];
+    if (L.rescan == 0) {
+      const int n = topk_idx[(size_t)b * p.K + r];
+      const int hw = n / L.A;
+      float x[C > 0 ? C : 1];
+      k1_load_logits<C>(L, b, n - hw * L.A, hw, x);
+      if (C == 0) tile_row = score_rows + ((size_t)b * p.K + r) * p.C;
+      k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
+                           row_argmax, x, tile_row, ncand, bmax, srow);
+    }
+  }
+  if constexpr (C > 0) k1_flush_rows<C>(tile + (threadIdx.x & ~31) * K1Tile<C>::stride, srow);
+  k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c (rescan form): levels where most priors are kept (no top-k at all, or k >= N/8) are walked
+// a second time with K1a's coalesced tiling; a prior finds its row arithmetically (no top-k:
+// row = k_off + n) or through the inverse map K1b scattered (row or -1).  Traffic = the level's
+// logits once more, instead of 8x that for a sector-granular gather.
+// ------------------------------------------------------------------------------------------
+template <int C, int HEAD>
+__global__ void __launch_bounds__(kK1aThreads)
+k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
+                  const float* __restrict__ scale_factors, const int* __restrict__ inv_map,
+                  int* __restrict__ topk_idx, float* __restrict__ score_rows, float* __restrict__ lam_rows,
+                  float* __restrict__ boxes, float* __restrict__ row_max, int* __restrict__ row_argmax,
+                  unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
+                  unsigned* __restrict__ cand_maxc) {
+  const int t = blockIdx.x;
+  const int b = t / p.rtiles_per_image;
+  const int ti = t - b * p.rtiles_per_image;
+  int s = -1;
+#pragma unroll
+  for (int i = 0; i < kMaxLevels; ++i)
+    if (i < p.S && p.lv[i].rescan && ti >= p.lv[i].rtile0) s = i;
+  const LevelDev& L = p.lv[s];
+  const int lt = ti - L.rtile0;
+  const int a = lt / L.tpp;
+  const int hw = (lt - a * L.tpp) * kK1aThreads + threadIdx.x;
+  int ncand = 0, r = -1;
+  float bmax = 0.f;
+  float* srow = nullptr;
+  __shared__ float tile[(C > 0) ? (kK1aThreads * K1Tile<C>::stride) : 1];
+  float* tile_row = (C > 0) ? tile + threadIdx.x * K1Tile<C>::stride : nullptr;
+  if (hw < L.HW) {
+    const int n = hw * L.A + a;
+    float x[C > 0 ? C : 1];
+    k1_load_logits<C>(L, b, a, hw, x);      // every thread loads: full coalesced lines, as in K1a
+    if (L.topk) {
+      r = inv_map[(size_t)b * p.N + L.n_off + a * L.HW + hw];
+    } else {
+      r = L.k_off + n;
+      topk_idx[(size_t)b * p.K + r] = n;
+    }
+    if (r >= 0) {
+      if (C == 0) tile_row = score_rows + ((size_t)b * p.K + r) * p.C;
+      k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
+                           row_argmax, x, tile_row, ncand, bmax, srow);
+    }
+  }
+  if constexpr (C > 0) k1_flush_rows<C>(tile + (threadIdx.x & ~31) * K1Tile<C>::stride, srow);
+  k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
 }
 
 }  // namespace mehhua

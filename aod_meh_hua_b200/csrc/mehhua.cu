@@ -74,7 +74,7 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   memset(&p, 0, sizeof(p));
   p.S = cfg->num_levels; p.B = B; p.C = cfg->c_out; p.head = cfg->head;
   p.num_fg = cfg->head == MEHHUA_HEAD_SSD ? cfg->c_out - 1 : cfg->c_out;
-  long long n_off = 0, k_off = 0, tile0 = 0;
+  long long n_off = 0, k_off = 0, tile0 = 0, rtile0 = 0;
   for (int s = 0; s < p.S; ++s) {
     LevelDev& L = p.lv[s];
     if (lv[s].H < 1 || lv[s].W < 1 || lv[s].A < 1) return arg_fail("level geometry");
@@ -91,10 +91,15 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
     L.n_off = (int)n_off; L.k_off = (int)k_off;
     L.tpp = (L.HW + kK1aThreads - 1) / kK1aThreads;
     L.tile0 = (int)tile0;
+    // rows of a level come from the coalesced rescan when many priors are kept: the gather touches one
+    // 32-byte sector (64-byte DRAM burst) per 4-byte logit, i.e. 8-16x the bytes it needs
+    L.rescan = (!L.topk || 2ll * L.k >= n) ? 1 : 0;
+    L.rtile0 = (int)rtile0;
+    if (L.rescan) rtile0 += (long long)L.tpp * L.A;
     n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
   }
   if (n_off > (1ll << 30) || k_off > (1 << 20) || tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
-  p.N = (int)n_off; p.K = (int)k_off; p.tiles_per_image = (int)tile0;
+  p.N = (int)n_off; p.K = (int)k_off; p.tiles_per_image = (int)tile0; p.rtiles_per_image = (int)rtile0;
   p.row_stride = cfg->mode == MEHHUA_MODE_ALL ? cfg->pair_cap : p.K;
   if (cfg->mode == MEHHUA_MODE_ALL)
     for (int s = 0; s < p.S; ++s)
@@ -123,6 +128,7 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   const size_t o_maxc = take((size_t)p.B * sizeof(unsigned));
   const size_t o_status = take(sizeof(unsigned));
   const size_t o_work = take(4 * sizeof(int));
+  const size_t o_inv = take((size_t)p.B * p.N * sizeof(int));
   const size_t o_fgl = take((size_t)p.B * p.pair_cap * sizeof(unsigned));
   const size_t o_fgc = take((size_t)p.B * sizeof(int));
   const size_t o_lamp = take((size_t)p.B * p.tiles_per_image * sizeof(float));
@@ -134,6 +140,7 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
     ws->cand_maxc = reinterpret_cast<unsigned*>(b + o_maxc);
     ws->status = reinterpret_cast<unsigned*>(b + o_status);
     ws->work_counter = reinterpret_cast<int*>(b + o_work);
+    ws->inv_map = reinterpret_cast<int*>(b + o_inv);
     ws->fg_list = reinterpret_cast<unsigned*>(b + o_fgl);
     ws->fg_cnt = reinterpret_cast<int*>(b + o_fgc);
     ws->lam_part = reinterpret_cast<float*>(b + o_lamp);
@@ -206,14 +213,24 @@ int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes,
       CU(cudaFuncSetAttribute(k1b_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
       attr = true;
     }
-    k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.status);
+    k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.inv_map, ws.status);
     LAUNCHED("k1b_select_kernel");
   }
   timer_mark(st, 2);
-  k1c_gather_kernel<C, HEAD><<<dim3((p.K + kGatherThreads - 1) / kGatherThreads, p.B), kGatherThreads, 0, st>>>(
-      p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
-      o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
-  LAUNCHED("k1c_gather_kernel");
+  bool any_gather = false;
+  for (int s = 0; s < p.S; ++s) any_gather |= p.lv[s].rescan == 0;
+  if (any_gather) {
+    k1c_gather_kernel<C, HEAD><<<dim3((p.K + kGatherThreads - 1) / kGatherThreads, p.B), kGatherThreads, 0, st>>>(
+        p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
+        o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
+    LAUNCHED("k1c_gather_kernel");
+  }
+  if (p.rtiles_per_image > 0) {
+    k1c_rescan_kernel<C, HEAD><<<p.B * p.rtiles_per_image, kK1aThreads, 0, st>>>(
+        p, img_shapes, scale_factors, ws.inv_map, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
+        o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
+    LAUNCHED("k1c_rescan_kernel");
+  }
   return 0;
 }
 
