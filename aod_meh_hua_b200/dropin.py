@@ -10,9 +10,10 @@ tools/train_RetinaNet.py / tools/train_SSD.py keep working unchanged:
   update_X_L                            <- mmdet/utils/active_datasets.py:102-135 (pool.py)
 
 The mixin goes in front of the reference head in the MRO (`class Lambda_L2Net_B200(
-B200ScoringMixin, Lambda_L2Net)`, see register_heads / INTEGRATION.md).  Only the Entropy_NMS
-scoring route is taken over; every other route (evaluation with isEval=True, Entropy_ALL,
-ONNX export) falls through to the reference method via super().
+B200ScoringMixin, Lambda_L2Net)`, see register_heads / INTEGRATION.md).  Taken over: the Entropy_NMS
+and Entropy_ALL scoring routes and the plain evaluation route (isEval=True -> det_results from
+K1 + K3a); everything else (Entropy_NoNMS, ONNX export, a non-default cfg) falls through to the
+reference method via super().
 """
 from __future__ import annotations
 
@@ -52,20 +53,30 @@ class B200ScoringMixin:
 
     mehhua_params = ScoringParams()     # reference constants; override per class / instance for ablations
     mehhua_max_batch = 8
+    # Lambda_L2_ReLU / _ablation read the object / foreground thresholds from kwargs['score_thr'] and
+    # the cluster IoU from kwargs['iou_thr'] (Lambda_L2_ReLU.py:150-154, 395-398); Lambda_L2Net and
+    # MyLSSDHead ignore those kwargs and hard-code 0.3 / 0.5 (Lambda_L2.py:349, 500, 508)
+    mehhua_thresholds_from_kwargs = False
+    mehhua_fused_eval = True            # isEval route: detections from K1 + K3a instead of super()
     _mehhua_scorers: Dict[tuple, Scorer]
 
-    def _mehhua_scorer(self, cls_scores: List[torch.Tensor], img_hw, uPool2: str, clsW: bool) -> Scorer:
+    def _mehhua_scorer(self, cls_scores: List[torch.Tensor], img_hw, uPool2: str, clsW: bool, kwargs=None) -> Scorer:
         B = cls_scores[0].shape[0]
+        p = self.mehhua_params
+        if self.mehhua_thresholds_from_kwargs and kwargs:
+            thr = kwargs.get("score_thr") or 0.3
+            iou = kwargs.get("iou_thr") or 0.5
+            p = ScoringParams(n_samples=p.n_samples, fg_thr=thr, obj_thr=thr, cluster_iou=iou,
+                              lambda_scale=p.lambda_scale, lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, seed=p.seed)
         featmaps = [tuple(c.shape[-2:]) for c in cls_scores]
         c_out = int(self.cls_out_channels)
         num_anchors = [c.shape[1] // c_out for c in cls_scores]
         device = cls_scores[0].device
         key = (tuple(featmaps), tuple(num_anchors), c_out, str(device), uPool2, bool(clsW),
-               max(B, self.mehhua_max_batch))
+               max(B, self.mehhua_max_batch), p.fg_thr, p.obj_thr, p.cluster_iou)
         cache = self.__dict__.setdefault("_mehhua_scorers", {})
         if key not in cache:
             spec = _spec_from_head(self, featmaps, num_anchors, img_hw)
-            p = self.mehhua_params
             params = ScoringParams(n_samples=p.n_samples, fg_thr=p.fg_thr, obj_thr=p.obj_thr,
                                    cluster_iou=p.cluster_iou, lambda_scale=p.lambda_scale,
                                    lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, agg=uPool2,
@@ -83,6 +94,14 @@ class B200ScoringMixin:
                 and "L_scores" in kwargs and (cfg is None or cfg is self.test_cfg):
             return self._mehhua_entropy_all(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes,
                                             scale_factors, **kwargs)
+        if (not kwargs.get("isUnc")) and with_nms and self.mehhua_fused_eval and (cfg is None or cfg is self.test_cfg) \
+                and not torch.onnx.is_in_onnx_export() and mlvl_cls_scores[0].is_cuda:
+            # evaluation route (isEval=True, isUnc=None; eval hook -> single_gpu_test): plain det_results
+            hw = tuple(int(v) for v in img_shapes[0][:2])
+            sc = self._mehhua_scorer(list(mlvl_cls_scores), hw, ScoringParams().agg, False)
+            if bool(sc.cfg.rescale) != bool(rescale):
+                sc.cfg.rescale = int(bool(rescale))
+            return sc.detect(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors)
         if not scoring or (cfg is not None and cfg is not self.test_cfg):
             return super()._get_bboxes(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors,
                                        cfg, rescale, with_nms, **kwargs)
@@ -90,7 +109,7 @@ class B200ScoringMixin:
             raise NotImplementedError("scaleUnc=True is undefined on the Entropy_NMS route of the reference")
         B = mlvl_cls_scores[0].shape[0]
         hw = tuple(int(v) for v in img_shapes[0][:2])
-        sc = self._mehhua_scorer(list(mlvl_cls_scores), hw, kwargs["uPool2"], kwargs.get("clsW", False))
+        sc = self._mehhua_scorer(list(mlvl_cls_scores), hw, kwargs["uPool2"], kwargs.get("clsW", False), kwargs)
         if bool(sc.cfg.rescale) != bool(rescale):
             sc.cfg.rescale = int(bool(rescale))
         ids = kwargs.get("image_ids")

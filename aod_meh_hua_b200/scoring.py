@@ -253,6 +253,18 @@ class Scorer:
                                    "re-create the Scorer with a larger pair_cap")
         return st
 
+    def detect(self, cls_scores, bbox_preds, anchors, img_shapes, scale_factors):
+        """Detections only (K1 + K3a), the isEval=True route of _get_bboxes (Lambda_L2.py:383-384):
+        list of (Tensor[n,5], LongTensor[n]).  No lambda map is needed; the logits tensor stands in
+        for it (K1c only copies it into lam_rows, which this route ignores)."""
+        self.bind(cls_scores, bbox_preds, [c[:, : c.shape[1] // self.spec.c_out] for c in cls_scores], anchors,
+                  img_shapes, scale_factors)
+        self.k1()
+        self.nms()
+        res = self.result()
+        n_det = res.n_det.cpu().tolist()
+        return [(res.dets[b, :n_det[b]].clone(), res.det_labels[b, :n_det[b]].long()) for b in range(res.B)]
+
     def result(self) -> BatchResult:
         B = self._B
         return BatchResult(B=B, **{k: v[:B] for k, v in self.t.items()})

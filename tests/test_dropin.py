@@ -67,7 +67,13 @@ def test_get_bboxes_route(spec_name):
         np.testing.assert_allclose(d.cpu().numpy(), out["dets"][b].numpy(), rtol=1e-5, atol=1e-4)
     # free-running sampler vs the oracle's own Monte-Carlo draw: same estimator, different stream
     np.testing.assert_allclose(unc, out["image_scores"], rtol=0.15, atol=0.05)
-    # every other route falls through to the reference method
+    # evaluation route (isEval=True, isUnc=None): plain det_results from the fused decode + NMS
+    ev = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, isUnc=None, isEval=True)
+    assert len(ev) == 2
+    for b, (d, l) in enumerate(ev):
+        assert np.array_equal(l.cpu().numpy(), out["labels"][b].numpy())
+        np.testing.assert_allclose(d.cpu().numpy(), out["dets"][b].numpy(), rtol=1e-5, atol=1e-4)
+    head.mehhua_fused_eval = False      # opt-out: every other route falls through to the reference method
     assert head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, isUnc=None, isEval=True) == "reference-route"
     kw2 = dict(KW, uPool="Entropy_NoNMS")
     assert head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam, **kw2) == "reference-route"
@@ -241,3 +247,35 @@ def test_all_equal_keys_take_the_tie_breaking_passes():
     res2 = sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
                     batch["scale_factors"], check=False)
     assert np.array_equal(res2.topk_idx.cpu().numpy(), res.topk_idx.cpu().numpy())
+
+
+def test_ablation_variant_parameters():
+    """Lambda_L2_ReLU-style variants: thresholds from kwargs (score_thr -> object / foreground
+    threshold, iou_thr -> cluster IoU) and no lambda scaling (Lambda_L2_noL.py:531)."""
+    from aod_meh_hua_b200.scoring import Scorer
+    from tests.helpers import check_topk_order, injection_buffers
+    spec, batch = make_batch("tiny_retina_coco", [0, 1, 2])
+    params = ScoringParams(fg_thr=0.2, obj_thr=0.2, cluster_iou=0.4, use_lambda=False, n_samples=50)
+    out, rec = run_oracle(spec, batch, params)
+    sc = Scorer(spec, params, max_batch=3, device="cuda:0")
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                batch["scale_factors"], image_ids=batch["gids"])
+    sc.k1(); torch.cuda.synchronize()
+    override, swapped = check_topk_order(spec, out, sc.result().topk_idx.cpu().numpy())
+    if swapped:
+        out, rec = run_oracle(spec, batch, params, topk_override=override)
+    sc.nms(); sc.pairs()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off); sc.hua()
+    np.testing.assert_allclose(sc.result().image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float32),
+                               rtol=1e-5, atol=1e-5)
+    # the mixin picks the thresholds up from kwargs when the variant flag is set
+    head = _head(spec)
+    head.mehhua_thresholds_from_kwargs = True
+    head.mehhua_params = ScoringParams(use_lambda=False)
+    cls, reg, lam, anc = _cuda(batch)
+    sf = [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]]
+    kw = dict(KW, score_thr=0.2, iou_thr=0.4)
+    _, unc = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, L_scores=lam, **kw)
+    want = run_oracle(spec, batch, ScoringParams(fg_thr=0.2, obj_thr=0.2, cluster_iou=0.4, use_lambda=False))[0]["image_scores"]
+    np.testing.assert_allclose(unc, want, rtol=0.15, atol=0.05)
