@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--ring", type=int, default=0, help="distinct resident images per GPU (0 = auto)")
     ap.add_argument("--samples", type=int, default=500, help="Dirichlet samples T (reference: 500)")
     ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-batch", type=int, default=32, help="images per host-buffer call")
     ap.add_argument("--cpu-images", type=int, default=4, help="images of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -292,7 +293,7 @@ def main():
     # ---- e2e: host buffers through mehhua_score_batch_host (pinned inputs, H2D + D2H timed)
     e2e = None
     if rank == 0 or world > 1:
-        Be = min(B, 8)
+        Be = min(B, args.e2e_batch)
         ctx = C.c_void_p()
         _lib.check(lib.mehhua_host_ctx_create(C.byref(sc.cfg), sc._shape_levels, Be, C.byref(ctx)), "host_ctx_create")
         h_cls = [c[:Be].cpu().pin_memory() for c in cls]
