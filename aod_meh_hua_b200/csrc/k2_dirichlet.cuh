@@ -56,7 +56,7 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
 __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // per-warp shared memory, in floats:
-//   cst4[C] (float4: b, 1/alpha, alpha-1, -b) | lbuf[C*33] | alpha[C] | avg[C] | lists 3 x C bytes
+//   cst4[C] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*33] | alpha[C] | avg[C] | lists 3 x C bytes
 __host__ __device__ inline size_t k2_warp_floats(int C) {
   const size_t f = 4 * (size_t)C + (size_t)C * kLStride + 2 * (size_t)C + (3 * (size_t)C + 3) / 4;
   return (f + 3) & ~(size_t)3;
@@ -69,14 +69,12 @@ __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_wa
 //   p = b*U1;  p <= 1: x = p^(1/alpha), accept iff U2 <= exp(-x)
 //              p >  1: x = -ln((b-p)/alpha) >= 1, accept iff U2 <= x^(alpha-1)
 // both tests are done as log2(U2) <= rhs.
-__device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const unsigned w0, const unsigned w1,
+__device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const float f0, const float f1,
                                            const unsigned s_small, const unsigned s_cst4, unsigned& c, float& l2) {
-  c = lds_u8(s_small + min(i, nsmall - 1));
-  const float4 k = lds_v4(s_cst4 + c * 16u);            // b, 1/alpha, alpha-1, -b
-  // uniforms straight from the bits: f = 1.mantissa in [1,2), U = f - 1 (23-bit resolution), no
-  // int->float conversion on the SFU pipe
-  const float f0 = __uint_as_float(0x3f800000u | (w0 >> 9));
-  const float f1 = __uint_as_float(0x3f800000u | (w1 >> 9));
+  // f0, f1 in [1,2): U1 = f0 - 1 (22-bit resolution), U2 = f1 - 1 + 2^-21 in (0,1) (20-bit)
+  const unsigned ii = (unsigned)min(i, nsmall - 1);
+  c = lds_u8(s_small + ii);
+  const float4 k = lds_v4(s_cst4 + ii * 16u);           // b, 1/alpha, alpha-1, -b (list order)
   const float pp = fmaf(f0, k.x, k.w);                  // b * U1
   const bool lo = pp <= 1.f;
   const float q = lo ? pp : (k.x - pp) * k.y;
@@ -87,11 +85,21 @@ __device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const 
   const float rhsb = k.z * l2b;                         // log2 x^(alpha-1)
   l2 = lo ? l2a : l2b;
   const float rhs = lo ? rhsa : rhsb;
-  // U2 = f1 - 1 + 2^-24 in (0,1): log2(U2) <= rhs
-  return (i < nsmall) & (lg2_approx(f1 - 0.99999994f) <= rhs);
+  return (i < nsmall) & (lg2_approx(f1 - 0.99999952316284180f) <= rhs);   // f1 - (1 - 2^-21)
 }
 
-__global__ void __launch_bounds__(kK2Threads)
+// One Philox4x32 block (128 bits) -> three (U1, U2) pairs: 22 + 20 bits each, as floats in [1,2)
+// built straight from the bits (no int->float conversion on the SFU pipe).
+__device__ __forceinline__ void split_block(const uint4 w, float (&f0)[3], float (&f1)[3]) {
+  f0[0] = __uint_as_float(0x3f800000u | ((w.x >> 9) & 0x7ffffeu));                         // w.x[31:10]
+  f1[0] = __uint_as_float(0x3f800000u | ((__funnelshift_r(w.y, w.x, 22) & 0xfffffu) << 3)); // w.x[9:0] : w.y[31:22]
+  f0[1] = __uint_as_float(0x3f800000u | ((w.y << 1) & 0x7ffffeu));                         // w.y[21:0]
+  f1[1] = __uint_as_float(0x3f800000u | ((w.z >> 9) & 0x7ffff8u));                         // w.z[31:12]
+  f0[2] = __uint_as_float(0x3f800000u | ((__funnelshift_r(w.w, w.z, 22) & 0x3fffffu) << 1)); // w.z[11:0] : w.w[31:22]
+  f1[2] = __uint_as_float(0x3f800000u | ((w.w << 1) & 0x7ffff8u));                         // w.w[21:2]
+}
+
+__global__ void __launch_bounds__(kK2Threads, 2)
 k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ score_rows,
                     const float* __restrict__ lam_rows, const float* __restrict__ lam_mean,
                     const int* __restrict__ pair_row, const int* __restrict__ pair_obj,
@@ -158,12 +166,15 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       const bool small = valid && !bad && a < 1.f;
       const unsigned mb = __ballot_sync(full, big), ms = __ballot_sync(full, small), mx = __ballot_sync(full, bad);
       if (big) s_big[nbig + __popc(mb & lt_mask)] = (unsigned char)c;
-      if (small) s_small[nsmall + __popc(ms & lt_mask)] = (unsigned char)c;
+      if (small) {      // list entry = class id; the GS constants sit at the same list position
+        const int pos = nsmall + __popc(ms & lt_mask);
+        const float bb = fmaf(a, kInvE, 1.f);
+        s_small[pos] = (unsigned char)c;
+        cst4[pos] = make_float4(bb, __fdiv_rn(1.f, a), a - 1.f, -bb);
+      }
       if (bad) s_bad[nbad + __popc(mx & lt_mask)] = (unsigned char)c;
       nbig += __popc(mb); nsmall += __popc(ms); nbad += __popc(mx);
       if (valid) {
-        const float bb = fmaf(a, kInvE, 1.f);
-        cst4[c] = make_float4(bb, bad ? 0.f : __fdiv_rn(1.f, a), a - 1.f, -bb);
         s_alpha[c] = bad ? 0.f : a;
         s_avg[c] = 0.f;
       }
@@ -221,49 +232,43 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
             m = fmaxf(m, l2);
           }
         }
-        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with four cursors (list positions
-        // mod 4): each iteration two Philox blocks feed one attempt per cursor, so a lane never idles
-        // while a neighbour retries and the four attempts overlap in the pipelines.
-        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall, ic = active ? 2 : nsmall, id = active ? 3 : nsmall;
+        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with three cursors (list positions
+        // mod 3): each iteration one Philox block (128 bits = 3 x (22 + 20)) feeds one attempt per
+        // cursor, so a lane never idles while a neighbour retries and the attempts overlap in the pipes.
+        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall, ic = active ? 2 : nsmall;
         unsigned kcall = 0;
         if (nsmall > 0) {
-          while (__any_sync(full, (ia < nsmall) | (ib < nsmall) | (ic < nsmall) | (id < nsmall))) {
-            const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall, pid, gid), key);
-            const uint4 v = philox4x32_10(make_uint4((unsigned)t, kcall + 1u, pid, gid), key);
-            kcall += 2u;
-            unsigned ca, cb, cc, cd;
-            float la, lb, lc, ld;
-            const bool oka = gs_attempt(ia, nsmall, w.x, w.y, a_small, a_cst4, ca, la);
-            const bool okb = gs_attempt(ib, nsmall, w.z, w.w, a_small, a_cst4, cb, lb);
-            const bool okc = gs_attempt(ic, nsmall, v.x, v.y, a_small, a_cst4, cc, lc);
-            const bool okd = gs_attempt(id, nsmall, v.z, v.w, a_small, a_cst4, cd, ld);
-            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), la); m = fmaxf(m, la); ia += 4; }
-            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), lb); m = fmaxf(m, lb); ib += 4; }
-            if (okc) { sts_f32(a_lrow + cc * (kLStride * 4u), lc); m = fmaxf(m, lc); ic += 4; }
-            if (okd) { sts_f32(a_lrow + cd * (kLStride * 4u), ld); m = fmaxf(m, ld); id += 4; }
+          while (__any_sync(full, (ia < nsmall) | (ib < nsmall) | (ic < nsmall))) {
+            float f0[3], f1[3];
+            split_block(philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key), f0, f1);
+            unsigned ca, cb, cc;
+            float la, lb, lc;
+            const bool oka = gs_attempt(ia, nsmall, f0[0], f1[0], a_small, a_cst4, ca, la);
+            const bool okb = gs_attempt(ib, nsmall, f0[1], f1[1], a_small, a_cst4, cb, lb);
+            const bool okc = gs_attempt(ic, nsmall, f0[2], f1[2], a_small, a_cst4, cc, lc);
+            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), la); m = fmaxf(m, la); ia += 3; }
+            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), lb); m = fmaxf(m, lb); ib += 3; }
+            if (okc) { sts_f32(a_lrow + cc * (kLStride * 4u), lc); m = fmaxf(m, lc); ic += 3; }
           }
         }
         __syncwarp();
-        // normalise in log space.  e_c = 2^(l_c - m); A = sum e = 1 + A' with the max term kept out
-        // of the sum (log1p keeps ln A accurate when one class owns the sample);
+        // normalise in log space.  e_c = 2^(l_c - m), A = sum e (>= 1: the max term is exactly 1);
         // -sum_c x ln x = ln A - ln2 * (sum_c e_c d_c) / A with d_c = l_c - m (log2 units)
         float inv_a = 0.f;
         if (active) {
           if (!(m > -INFINITY)) m = 0.f;
-          float ap = 0.f, bs = 0.f;
-          int nzero = 0;
+          float asum = 0.f, bs = 0.f;
           unsigned addr = a_lrow;
           for (int c = 0; c < C; ++c, addr += kLStride * 4u) {
             const float d = fmaxf(lds_f32(addr) - m, -300.f);
             const float e = ex2_approx(d);
-            if (d == 0.f) ++nzero; else ap += e;
+            asum += e;
             bs = fmaf(e, d, bs);
             sts_f32(addr, e);
           }
-          if (nzero > 0) {
-            ap += (float)(nzero - 1);
-            inv_a = __fdividef(1.f, 1.f + ap);
-            ent_acc += log1pf(ap) - kLn2 * bs * inv_a;
+          if (asum > 0.f) {
+            inv_a = __fdividef(1.f, asum);
+            ent_acc += logf(asum) - kLn2 * bs * inv_a;
           }
         } else {
           unsigned addr = a_lrow;
