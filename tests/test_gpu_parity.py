@@ -301,3 +301,26 @@ def test_many_pairs_take_the_object_range_rounds():
     np.testing.assert_allclose(res.pair_unc[0, :n_pairs, 2].cpu().numpy(), epi, rtol=1e-4, atol=5e-6)
     np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float32),
                                rtol=RTOL, atol=1e-4)
+
+
+def test_repeated_calls_are_bitwise_reproducible():
+    """The same Scorer called again (same images, then other images) gives bit-identical outputs to a
+    fresh Scorer: no state leaks between calls through the workspace."""
+    spec, b1 = make_batch("cfg1_retina_r50_512_voc", [0, 1])
+    _, b2 = make_batch("cfg1_retina_r50_512_voc", [2, 3])
+    params = ScoringParams(n_samples=40)
+    fresh = lambda: Scorer(spec, params, max_batch=2, device="cuda:0")
+    def run(sc, b):
+        r = sc.score(b["cls_scores"], b["bbox_preds"], b["L_scores"], b["anchors"], b["img_shapes"],
+                     b["scale_factors"], image_ids=b["gids"])
+        torch.cuda.synchronize()
+        return {k: getattr(r, k).cpu().numpy().copy() for k in ("score_rows", "topk_idx", "boxes", "row_max", "dets",
+                                                                  "det_flat", "n_det", "pair_off", "image_scores")}
+    ref1, ref2 = run(fresh(), b1), run(fresh(), b2)
+    sc = fresh()
+    run(sc, b1)
+    again1 = run(sc, b1)
+    again2 = run(sc, b2)
+    for k in ref1:
+        assert np.array_equal(again1[k], ref1[k]), k
+        assert np.array_equal(again2[k], ref2[k]), k
