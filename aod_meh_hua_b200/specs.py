@@ -166,6 +166,9 @@ SPECS = {
     "tiny_retina_voc": retina_spec("tiny_retina_voc", 128, 160, 20, gt_range=(1, 4)),
     "tiny_retina_coco": retina_spec("tiny_retina_coco", 96, 128, 80, gt_range=(1, 3)),
     "tiny_ssd_voc": ssd_spec("tiny_ssd_voc", 300, 20, gt_range=(1, 4)),
+    # class counts without a template instantiation (generic kernels)
+    "tiny_retina_c12": retina_spec("tiny_retina_c12", 96, 128, 12, gt_range=(1, 3)),
+    "tiny_ssd_c7": ssd_spec("tiny_ssd_c7", 300, 7, gt_range=(1, 4)),
 }
 
 

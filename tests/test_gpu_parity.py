@@ -18,6 +18,8 @@ CASES = [
     ("tiny_retina_coco", [0, 1, 2], (1.0, 1.0, 1.0, 1.0)),
     ("tiny_ssd_voc", [0, 1], (1.0, 1.0, 1.0, 1.0)),
     ("tiny_retina_coco", [3, 4], (1.07, 0.94, 1.07, 0.94)),
+    ("tiny_retina_c12", [0, 1, 2], (1.0, 1.0, 1.0, 1.0)),       # generic (runtime class count) kernels
+    ("tiny_ssd_c7", [0, 1], (1.0, 1.0, 1.0, 1.0)),
 ]
 
 
@@ -204,6 +206,7 @@ def test_sampler_moments_across_alpha_regimes():
 
 
 @pytest.mark.parametrize("spec_name,kind", [("tiny_retina_coco", "scaleAvg_classAvg"), ("tiny_ssd_voc", "scaleSum_classSum"),
+                                            ("tiny_retina_c12", "scaleSum_classSum"), ("tiny_ssd_c7", "scaleAvg_classAvg"),
                                             ("tiny_retina_voc", "scaleSum_classAvg"), ("tiny_retina_coco", "scaleAvg_classSum")])
 def test_entropy_all_mode_parity(spec_name, kind):
     """Entropy_ALL route (ComputeScaleUnc + AggregateScaleUnc): foreground prior lists, class keys,
