@@ -208,10 +208,17 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
         const bool active = t < T;
-        float m = -INFINITY;
+        // Normalisation is a log-sum-exp around a reference exponent m fixed BEFORE the bulk of the
+        // draws: the largest of the alpha >= 1 draws (they own the sample; 0 when there are none).
+        //   e_c = 2^(l_c - m),  A = sum_c e_c,  x_c = e_c / A,
+        //   -sum_c x ln x = ln A - ln2 * (sum_c e_c d_c) / A   with d_c = l_c - m (log2 units)
+        // Any m gives the same value; fixing it early lets every accepted draw be folded into A and
+        // the entropy sum on the spot, so the draws are stored as e_c and read back only once.
+        float m = 0.f, asum = 0.f, bs = 0.f;
         if (active) {
-          for (int i = 0; i < nbad; ++i) lbuf[s_bad[i] * kLStride + lane] = -INFINITY;
+          for (int i = 0; i < nbad; ++i) lbuf[s_bad[i] * kLStride + lane] = 0.f;
           // Marsaglia-Tsang for the few classes with alpha >= 1
+          float mbig = -INFINITY;
           for (int i = 0; i < nbig; ++i) {
             const int c = s_big[i];
             const float d = s_alpha[c] - (1.f / 3.f);
@@ -229,8 +236,20 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
               }
             }
             lbuf[c * kLStride + lane] = l2;
-            m = fmaxf(m, l2);
+            mbig = fmaxf(mbig, l2);
           }
+          if (nbig > 0) m = mbig;
+          for (int i = 0; i < nbig; ++i) {
+            const int c = s_big[i];
+            const float d = lbuf[c * kLStride + lane] - m;
+            const float e = ex2_approx(d);
+            asum += e;
+            bs = fmaf(e, d, bs);
+            lbuf[c * kLStride + lane] = e;
+          }
+        } else {
+          unsigned addr = a_lrow;
+          for (int c = 0; c < C; ++c, addr += kLStride * 4u) sts_f32(addr, 0.f);
         }
         // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with three cursors (list positions
         // mod 3): each iteration one Philox block (128 bits = 3 x (22 + 20)) feeds one attempt per
@@ -246,33 +265,17 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
             const bool oka = gs_attempt(ia, nsmall, f0[0], f1[0], a_small, a_cst4, ca, la);
             const bool okb = gs_attempt(ib, nsmall, f0[1], f1[1], a_small, a_cst4, cb, lb);
             const bool okc = gs_attempt(ic, nsmall, f0[2], f1[2], a_small, a_cst4, cc, lc);
-            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), la); m = fmaxf(m, la); ia += 3; }
-            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), lb); m = fmaxf(m, lb); ib += 3; }
-            if (okc) { sts_f32(a_lrow + cc * (kLStride * 4u), lc); m = fmaxf(m, lc); ic += 3; }
+            const float da = fmaxf(la - m, -300.f), db = fmaxf(lb - m, -300.f), dc = fmaxf(lc - m, -300.f);
+            const float ea = ex2_approx(da), eb = ex2_approx(db), ec = ex2_approx(dc);
+            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), ea); asum += ea; bs = fmaf(ea, da, bs); ia += 3; }
+            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), eb); asum += eb; bs = fmaf(eb, db, bs); ib += 3; }
+            if (okc) { sts_f32(a_lrow + cc * (kLStride * 4u), ec); asum += ec; bs = fmaf(ec, dc, bs); ic += 3; }
           }
         }
-        __syncwarp();
-        // normalise in log space.  e_c = 2^(l_c - m), A = sum e (>= 1: the max term is exactly 1);
-        // -sum_c x ln x = ln A - ln2 * (sum_c e_c d_c) / A with d_c = l_c - m (log2 units)
         float inv_a = 0.f;
-        if (active) {
-          if (!(m > -INFINITY)) m = 0.f;
-          float asum = 0.f, bs = 0.f;
-          unsigned addr = a_lrow;
-          for (int c = 0; c < C; ++c, addr += kLStride * 4u) {
-            const float d = fmaxf(lds_f32(addr) - m, -300.f);
-            const float e = ex2_approx(d);
-            asum += e;
-            bs = fmaf(e, d, bs);
-            sts_f32(addr, e);
-          }
-          if (asum > 0.f) {
-            inv_a = __fdividef(1.f, asum);
-            ent_acc += logf(asum) - kLn2 * bs * inv_a;
-          }
-        } else {
-          unsigned addr = a_lrow;
-          for (int c = 0; c < C; ++c, addr += kLStride * 4u) sts_f32(addr, 0.f);
+        if (active && asum > 0.f) {
+          inv_a = __fdividef(1.f, asum);
+          ent_acc += logf(asum) - kLn2 * bs * inv_a;
         }
         __syncwarp();
         // class sums over the 32 samples, transposed: lane = class, walk the samples
