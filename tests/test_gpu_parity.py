@@ -327,3 +327,36 @@ def test_repeated_calls_are_bitwise_reproducible():
     for k in ref1:
         assert np.array_equal(again1[k], ref1[k]), k
         assert np.array_equal(again2[k], ref2[k]), k
+
+
+def test_per_image_shapes_scale_factors_and_pair_overflow():
+    """Images of one batch with different img_shape (clip window) and scale_factor; and the loud
+    failure when an image produces more pairs than pair_cap."""
+    from aod_meh_hua_b200 import _lib
+    spec, batch = make_batch("tiny_retina_coco", [0, 1, 2])
+    batch["img_shapes"] = [(96, 128, 3), (80, 100, 3), (64, 128, 3)]
+    batch["scale_factors"] = [(1.0, 1.0, 1.0, 1.0), (1.25, 1.2, 1.25, 1.2), (0.5, 0.75, 0.5, 0.75)]
+    params = ScoringParams()
+    out, rec = run_oracle(spec, batch, params)
+    sc = Scorer(spec, params, max_batch=3, device="cuda:0")
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    sc.k1(); torch.cuda.synchronize()
+    override, swapped = check_topk_order(spec, out, sc.result().topk_idx.cpu().numpy())
+    if swapped:
+        out, rec = run_oracle(spec, batch, params, topk_override=override)
+    sc.nms(); sc.pairs()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off); sc.hua()
+    res = sc.result()
+    np.testing.assert_allclose(res.boxes.cpu().numpy(), out["boxes"].numpy(), rtol=RTOL, atol=1e-4)
+    for b in range(3):
+        n = int(res.n_det[b])
+        assert np.array_equal(res.det_flat[b, :n].cpu().numpy(), out["det_flat"][b].numpy())
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float32),
+                               rtol=RTOL, atol=1e-5)
+    # pair_cap too small -> MEHHUA_ST_PAIR_OVERFLOW -> exception, never a silently truncated score
+    small = Scorer(spec, params, max_batch=3, device="cuda:0", pair_cap=8)
+    with pytest.raises(_lib.MehhuaError):
+        small.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                    batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
