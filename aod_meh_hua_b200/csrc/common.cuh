@@ -142,6 +142,8 @@ __device__ __forceinline__ void block_bitonic_desc(unsigned long long* buf, int 
   }
 }
 
+constexpr int kSelUnroll = 4;    // loads in flight per thread in the select passes (they are latency-bound)
+
 // Radix-select digit schedules (MSB first) over a 64-bit composite.
 // schedule 0: composites whose two top bits are zero (positive floats < 2.0 in the high word):
 //             the first 12-bit digit is float bits 29..18 = exponent + 5 mantissa bits.
@@ -163,12 +165,12 @@ __device__ int block_collect_topk(Get get, int n, int k, unsigned long long hi,
     const int shift = kDigitShift[SCHED][pass], bits = kDigitBits[SCHED][pass], bins = 1 << bits;
     for (int i = threadIdx.x; i < bins; i += THREADS) hist[i] = 0;
     __syncthreads();
-    for (int i0 = threadIdx.x; i0 < n; i0 += THREADS * 4) {   // four independent loads in flight
-      unsigned long long e[4];
+    for (int i0 = threadIdx.x; i0 < n; i0 += THREADS * kSelUnroll) {   // kSelUnroll independent loads in flight
+      unsigned long long e[kSelUnroll];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const int i = i0 + u * THREADS; e[u] = (i < n) ? get(i) : 0ull; }
+      for (int u = 0; u < kSelUnroll; ++u) { const int i = i0 + u * THREADS; e[u] = (i < n) ? get(i) : 0ull; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < kSelUnroll; ++u)
         if (e[u] != 0ull && e[u] < hi && (e[u] & mask) == prefix)
           atomicAdd(&hist[(int)((e[u] >> shift) & (bins - 1))], 1);
     }
@@ -203,12 +205,12 @@ __device__ int block_collect_topk(Get get, int n, int k, unsigned long long hi,
   // compaction of every e in [prefix, hi)
   if (threadIdx.x == 0) sh[36] = 0;
   __syncthreads();
-  for (int i0 = threadIdx.x; i0 < n; i0 += THREADS * 4) {
-    unsigned long long e[4];
+  for (int i0 = threadIdx.x; i0 < n; i0 += THREADS * kSelUnroll) {
+    unsigned long long e[kSelUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * THREADS; e[u] = (i < n) ? get(i) : 0ull; }
+    for (int u = 0; u < kSelUnroll; ++u) { const int i = i0 + u * THREADS; e[u] = (i < n) ? get(i) : 0ull; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < kSelUnroll; ++u)
       if (e[u] != 0ull && e[u] < hi && e[u] >= prefix) {
         const int pos = atomicAdd(&sh[36], 1);
         if (pos < CAP) buf[pos] = e[u];

@@ -172,7 +172,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
 //   order - the order of FG_pos_bbox.nonzero().
 // Afterwards warp s averages lambda over level s's pairs (duplicates counted) in a fixed order.
 // ------------------------------------------------------------------------------------------
-constexpr int kPairThreads = 256;
+constexpr int kPairThreads = 512;
 constexpr int kPairChunk = 4 * kPairThreads;
 constexpr int kPairWords = MEHHUA_MAX_DETS / 32;
 constexpr size_t kPairSmem = MEHHUA_MAX_DETS * 16 + kPairChunk * 16 + kPairChunk * kPairWords * 4 + kPairChunk * 8;
