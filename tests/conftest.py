@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is a build artefact (git-ignored): build it once if the checkout lacks it
+    lib = os.path.join(ROOT, "aod_meh_hua_b200", "libmehhua.so")
+    if not os.path.isfile(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "aod_meh_hua_b200", "csrc")], check=False)
 
 
 def pytest_collection_modifyitems(config, items):
