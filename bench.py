@@ -207,9 +207,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     img_bytes = 4 * spec.num_priors * (spec.c_out + 5)
-    B = args.batch or max(1, min(128, int(8.8e9 // img_bytes)))       # <= 8.8 GB of head outputs per step
-    ring = args.ring or max(2 * B, ((int(17.6e9 // img_bytes)) // B) * B)
-    ring = max(B, (min(ring, 8 * B) // B) * B)
+    B = args.batch or max(1, min(256, int(17.6e9 // img_bytes)))      # <= 17.6 GB of head outputs per step
+    ring = args.ring or max(2 * B, ((int(35.2e9 // img_bytes)) // B) * B)
+    ring = max(B, (min(ring, 4 * B) // B) * B)
     pool_size = POOL_SIZES.get(spec.name, 100000)
     lo, hi = shard_range(pool_size, rank, world)
     synth, cls, reg, lam = build_ring(spec, ring, lo, device)
@@ -289,6 +289,33 @@ def main():
                     algorithmic_bytes_per_launch=k1a_bytes,
                     k1_stage_achieved=B * spec.k1_bytes_per_image() / k1_all_s / 1e9 if k1_all_s > 0 else 0.0,
                     stage_ms_per_step=stage_avg)
+
+    # ---- aggregation-stage kernels against the same HBM peak (tiny algorithmic traffic,
+    #      expected latency-bound - reported, not a target)
+    S_ = spec.num_levels
+    p_tot = float(sc.t["pair_off"][:B, S_].float().sum().item())
+    n_obj_tot = float(sc.t["n_obj"][:B].float().sum().item())
+    k3_bytes = 16.0 * (B * spec.k_tot + n_obj_tot) + 12.0 * p_tot + 4.0 * B
+    k3_s = (stage_avg["k3b_pairs"] + stage_avg["k3c_hua"]) * 1e-3
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pool_all = torch.rand(pool_size, device=device)
+    kk = max(1, int(0.025 * pool_size))
+    pool_topk(pool_all, kk)
+    t0e.record()
+    for _ in range(5):
+        pool_topk(pool_all, kk)
+    t1e.record()
+    torch.cuda.synchronize()
+    k4_s = t0e.elapsed_time(t1e) / 5 * 1e-3
+    k4_bytes = 4.0 * pool_size + 8.0 * kk
+    roofline["aggregation"] = dict(
+        k3_pairs_hua=dict(bytes_per_step=k3_bytes, ms=k3_s * 1e3, achieved=k3_bytes / k3_s / 1e9 if k3_s > 0 else 0.0,
+                          frac=(k3_bytes / k3_s / 1e9 / peak) if k3_s > 0 else 0.0, pairs_per_image=p_tot / B,
+                          note="latency-bound: one block per image"),
+        k4_pool_topk=dict(bytes_per_launch=k4_bytes, ms=k4_s * 1e3, achieved=k4_bytes / k4_s / 1e9,
+                          frac=k4_bytes / k4_s / 1e9 / peak, pool=pool_size, k=kk, note="single block, once per pool"),
+        k2_draws_per_s=(p_tot * params.n_samples * spec.c_out) / (stage_avg["k2_dirichlet"] * 1e-3)
+        if stage_avg["k2_dirichlet"] > 0 else 0.0)
 
     # ---- e2e: host buffers through mehhua_score_batch_host (pinned inputs, H2D + D2H timed)
     e2e = None
