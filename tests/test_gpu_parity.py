@@ -360,3 +360,27 @@ def test_per_image_shapes_scale_factors_and_pair_overflow():
     with pytest.raises(_lib.MehhuaError):
         small.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
                     batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+
+
+def test_pool_topk_randomised_against_numpy():
+    """K4 / block radix select on adversarial score distributions: heavy ties, negatives, NaNs,
+    denormals, constant arrays, k from 1 to beyond the number of candidates."""
+    from aod_meh_hua_b200.scoring import pool_topk
+    rs = np.random.RandomState(123)
+    cases = []
+    for n in (1, 7, 1000, 4097, 70001):
+        cases.append(rs.rand(n).astype(np.float32))
+        cases.append(np.round(rs.rand(n) * 4).astype(np.float32))                    # 5 distinct values
+        cases.append((rs.randn(n) * 1e-3).astype(np.float32))                        # negatives around zero
+        cases.append(np.full(n, 0.25, dtype=np.float32))                             # constant
+        x = rs.rand(n).astype(np.float32); x[rs.rand(n) < 0.1] = np.nan; cases.append(x)
+        cases.append((rs.rand(n) * 1e-40).astype(np.float32))                        # denormals
+    for x in cases:
+        n = len(x)
+        mask = rs.rand(n) < 0.7
+        for k in sorted({1, min(n, 17), min(n, 4096), min(n, 5000), n}):
+            got = pool_topk(torch.from_numpy(x).cuda(), k, torch.from_numpy(mask).cuda()).cpu().numpy()
+            cand = np.nonzero(mask & ~np.isnan(x))[0]
+            order = np.argsort(x[cand], kind="stable")
+            want = cand[order[-k:]][::-1] if k <= len(cand) else cand[order][::-1]
+            assert np.array_equal(got, want), (n, k, x[:5])
