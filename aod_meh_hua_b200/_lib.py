@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmehhua.so")
 MAX_LEVELS = 8
 MAX_DETS = 256
 MAX_NMS_PRE = 4096
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
 ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA = 1, 2, 4
@@ -45,7 +45,7 @@ class Config(C.Structure):
 
 BUFFER_FIELDS = ["score_rows", "lam_rows", "boxes", "topk_idx", "row_max", "row_argmax", "level_fg",
                  "dets", "det_labels", "det_flat", "n_det", "n_obj", "pair_row", "pair_obj",
-                 "pair_cls", "pair_off", "lam_mean", "pair_unc", "image_scores"]
+                 "pair_cls", "pair_off", "lam_mean", "pair_unc", "image_scores", "level_maxconf"]
 
 
 class Buffers(C.Structure):

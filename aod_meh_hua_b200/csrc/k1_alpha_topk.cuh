@@ -73,6 +73,17 @@ __device__ __forceinline__ void softmax_stream(const float* __restrict__ src, si
   m_out = m;
 }
 
+// getMaxConf (mmdet/utils/functions.py:467-476): the largest softmax probability of a prior is
+// exp(0) * inv = inv (the max-logit class, background included for SSD).  Positive floats order
+// like their bit patterns, so the level maximum is one warp REDUX and an atomicMax by one lane -
+// issued only when the (possibly stale, hence never too large) cached value would be raised, which
+// keeps the same-address atomic traffic to a few updates per (image, level).
+__device__ __forceinline__ void level_maxconf_update(unsigned* dst, float inv) {
+  const unsigned m = __activemask();
+  const unsigned v = __reduce_max_sync(m, __float_as_uint(inv));
+  if ((threadIdx.x & 31) == (__ffs(m) - 1) && v > *dst) atomicMax(dst, v);
+}
+
 // ------------------------------------------------------------------------------------------
 // K1a: stream every logit once.  Tile = 128 consecutive (h,w) positions of one (image, anchor)
 // plane; thread t owns position hw and reads its C class logits with stride H*W, so each warp
@@ -81,7 +92,8 @@ __device__ __forceinline__ void softmax_stream(const float* __restrict__ src, si
 // ------------------------------------------------------------------------------------------
 template <int C, int HEAD>
 __global__ void __launch_bounds__(kK1aThreads)
-k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* __restrict__ level_fg) {
+k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* __restrict__ level_fg,
+                unsigned* __restrict__ level_maxconf) {
   const int t = blockIdx.x;
   const int b = t / p.tiles_per_image;
   const int ti = t - b * p.tiles_per_image;
@@ -109,6 +121,7 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
   const float key = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pfg, den) : pfg;
   keys[(size_t)b * p.N + L.n_off + a * L.HW + hw] = key;
   if (pfg > p.fg_thr) level_fg[b * p.S + s] = 1;
+  if (level_maxconf) level_maxconf_update(level_maxconf + b * p.S + s, inv);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ constexpr size_t kAllSmem = (size_t)kAllSortCap * 8 + 64 * 4;
 template <int C, int HEAD>
 __global__ void __launch_bounds__(kK1aThreads)
 ka_fg_kernel(const __grid_constant__ Plan p, unsigned* __restrict__ fg_list, int* __restrict__ fg_cnt,
-             float* __restrict__ lam_part, unsigned* __restrict__ status) {
+             float* __restrict__ lam_part, unsigned* __restrict__ status, unsigned* __restrict__ level_maxconf) {
   __shared__ float wsum[kK1aThreads / 32];
   const int t = blockIdx.x;
   const int b = t / p.tiles_per_image;
@@ -55,6 +55,7 @@ ka_fg_kernel(const __grid_constant__ Plan p, unsigned* __restrict__ fg_list, int
       softmax_stream<HEAD>(src, (size_t)L.HW, CC, m, inv, den, pfg);
     }
     lam = __ldg(L.lam + (size_t)(b * L.A + a) * L.HW + hw);
+    if (level_maxconf) level_maxconf_update(level_maxconf + b * p.S + s, inv);
     if (pfg > p.fg_thr) {
       const int pos = atomicAdd(fg_cnt + b, 1);
       if (pos < p.pair_cap) fg_list[(size_t)b * p.pair_cap + pos] = ((unsigned)s << 28) | (unsigned)(hw * L.A + a);

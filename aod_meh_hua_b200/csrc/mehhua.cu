@@ -202,7 +202,8 @@ template <int C, int HEAD>
 int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes, const float* scale_factors,
                     const mehhua_buffers_t* o, cudaStream_t st) {
   timer_mark(st, 0);
-  k1a_keys_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(p, ws.keys, o->level_fg);
+  k1a_keys_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
+      p, ws.keys, o->level_fg, reinterpret_cast<unsigned*>(o->level_maxconf));
   LAUNCHED("k1a_keys_kernel");
   timer_mark(st, 1);
   bool any_topk = false;
@@ -241,6 +242,7 @@ int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const
       !o->level_fg)
     return arg_fail("null K1 output buffer");
   CU(cudaMemsetAsync(o->level_fg, 0, (size_t)p.B * p.S * sizeof(int), st));
+  if (o->level_maxconf) CU(cudaMemsetAsync(o->level_maxconf, 0, (size_t)p.B * p.S * sizeof(float), st));
   CU(cudaMemsetAsync(ws.cand_cnt, 0, (size_t)p.B * sizeof(int), st));
   CU(cudaMemsetAsync(ws.cand_maxc, 0, (size_t)p.B * sizeof(unsigned), st));
   if (p.head == MEHHUA_HEAD_RETINA) {
@@ -259,7 +261,8 @@ int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const
 
 template <int C, int HEAD>
 int launch_all_typed(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
-  ka_fg_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(p, ws.fg_list, ws.fg_cnt, ws.lam_part, ws.status);
+  ka_fg_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
+      p, ws.fg_list, ws.fg_cnt, ws.lam_part, ws.status, reinterpret_cast<unsigned*>(o->level_maxconf));
   LAUNCHED("ka_fg_kernel");
   static bool attr = false;
   if (!attr) {
@@ -278,6 +281,7 @@ int launch_all(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cu
       !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->lam_mean || !o->n_obj || !o->n_det)
     return arg_fail("null Entropy_ALL buffer");
   CU(cudaMemsetAsync(ws.fg_cnt, 0, (size_t)p.B * sizeof(int), st));
+  if (o->level_maxconf) CU(cudaMemsetAsync(o->level_maxconf, 0, (size_t)p.B * p.S * sizeof(float), st));
   if (p.head == MEHHUA_HEAD_RETINA) {
     switch (p.C) {
       case 20: return launch_all_typed<20, MEHHUA_HEAD_RETINA>(p, ws, o, st);
@@ -639,6 +643,7 @@ int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* lev
   b.pair_cls = reinterpret_cast<int32_t*>(a + o_pc);    b.pair_off = reinterpret_cast<int32_t*>(a + o_poff);
   b.lam_mean = reinterpret_cast<float*>(a + o_lm);      b.pair_unc = reinterpret_cast<float*>(a + o_pu);
   b.image_scores = reinterpret_cast<float*>(a + o_sc);
+  b.level_maxconf = nullptr;               // getMaxConf is not part of the host-buffer call
   c->img_shapes = reinterpret_cast<float*>(a + o_shp);
   c->scale_factors = reinterpret_cast<float*>(a + o_sf);
   c->image_ids = reinterpret_cast<int64_t*>(a + o_ids);

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .pool import update_X_L  # noqa: F401  (re-exported: same signature as the reference's)
+from .pool import ResumeCycle, ResumeCycle_WorkDir, save_cycle, scoring_stage, update_X_L  # noqa: F401  (re-exported)
 from .scoring import Scorer
 from .specs import HEAD_RETINA, HEAD_SSD, DetectorSpec, ScoringParams, parse_agg_spec
 
@@ -115,15 +115,15 @@ class B200ScoringMixin:
         ids = kwargs.get("image_ids")
         if ids is None and "batchIdx" in kwargs:
             ids = [int(kwargs["batchIdx"]) * B + j for j in range(B)]    # apis/test.py:115 batchIdx=i
+        sc.save_max_conf(bool(kwargs.get("saveMaxConf")))
         res = sc.score(mlvl_cls_scores, mlvl_bbox_preds, kwargs["L_scores"], mlvl_anchors, img_shapes,
                        scale_factors, image_ids=ids)
         n_det = res.n_det.cpu().tolist()
         det_results = [(res.dets[b, :n_det[b]].clone(), res.det_labels[b, :n_det[b]].long())
                        for b in range(B)]
         agged = [float(v) if v != 0 else 0 for v in res.image_scores.cpu().tolist()]
-        if kwargs.get("saveMaxConf"):
-            maxconf = max_conf(mlvl_cls_scores, int(self.cls_out_channels))[0]
-            return det_results, agged, maxconf
+        if kwargs.get("saveMaxConf"):      # getMaxConf, fused into the logits pass (K1a)
+            return det_results, agged, res.level_maxconf.max(dim=1)[0].tolist()
         return det_results, agged
 
     def _mehhua_entropy_all(self, mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors,
@@ -132,8 +132,8 @@ class B200ScoringMixin:
         returns (det_results, AggedUnc).  The reference's det_results on this route are the raw
         (boxes [N,4], scores [N,C+1]) of every prior, which no caller reads (apis/test.py:116 only
         takes len()); they are returned here with zero rows."""
-        if kwargs.get("scaleUnc") or kwargs.get("saveMaxConf"):
-            raise NotImplementedError("scaleUnc / saveMaxConf outputs of the Entropy_ALL route")
+        if kwargs.get("scaleUnc"):
+            raise NotImplementedError("scaleUnc output of the Entropy_ALL route")
         B = mlvl_cls_scores[0].shape[0]
         dev = mlvl_cls_scores[0].device
         hw = tuple(int(v) for v in img_shapes[0][:2])
@@ -152,11 +152,15 @@ class B200ScoringMixin:
         ids = kwargs.get("image_ids")
         if ids is None and "batchIdx" in kwargs:
             ids = [int(kwargs["batchIdx"]) * B + j for j in range(B)]
+        sc.save_max_conf(bool(kwargs.get("saveMaxConf")))
         res = sc.score(mlvl_cls_scores, mlvl_bbox_preds, kwargs["L_scores"], mlvl_anchors, img_shapes,
                        scale_factors, image_ids=ids)
         dets = [(torch.zeros(0, 4, device=dev), torch.zeros(0, c_out + (0 if getattr(self, "last_activation", "relu") == "softmax" else 1), device=dev))
                 for _ in range(B)]
-        return dets, [float(v) if v != 0 else 0 for v in res.image_scores.cpu().tolist()]
+        agged = [float(v) if v != 0 else 0 for v in res.image_scores.cpu().tolist()]
+        if kwargs.get("saveMaxConf"):
+            return dets, agged, res.level_maxconf.max(dim=1)[0].tolist()
+        return dets, agged
 
     # ------------------------------------------------------------------ narrowest boundary
     def ComputeObjUnc(self, mlvl_cls_scores, pos_bboxes, mlvl_scores, mlvl_Ls, mlvl_idces):
@@ -226,15 +230,15 @@ class B200ScoringMixin:
         return output
 
 
-def max_conf(mlvl_cls_scores, n_cls: int):
-    """getMaxConf (mmdet/utils/functions.py:467-476): per image max softmax probability over all
-    levels (only used when saveMaxConf=True; not on the hot path)."""
-    B = mlvl_cls_scores[0].size(0)
-    out = torch.zeros(B, len(mlvl_cls_scores), device=mlvl_cls_scores[0].device)
-    for s, cs in enumerate(mlvl_cls_scores):
-        x = cs.permute(0, 2, 3, 1).reshape(B, -1, n_cls)
-        out[:, s] = x.softmax(dim=-1).reshape(B, -1).max(dim=-1)[0]
-    return out.max(dim=-1)[0].tolist(), out
+def max_conf(scorer: Scorer):
+    """getMaxConf (mmdet/utils/functions.py:467-476) of the batch the scorer last processed:
+    (list of per-image maxima, Tensor[B, S] per level).  The maxima come out of the same pass over
+    the logits as the top-k keys (K1a / KA1), not from a second softmax pass; the scorer must have
+    had save_max_conf(True) set for that batch."""
+    if not scorer.bufs.level_maxconf:
+        raise _lib.MehhuaError("max_conf: save_max_conf(True) was not set on this scorer")
+    out = scorer.result().level_maxconf
+    return out.max(dim=-1)[0].tolist(), out.clone()
 
 
 def calculate_uncertainty(cfg, model, data_loader, **kwargs):
@@ -242,8 +246,10 @@ def calculate_uncertainty(cfg, model, data_loader, **kwargs):
     (apis/test.py:52-70, 90-135): loops the pool loader in order and returns the list of 0-d CPU
     tensors the AL scripts stack (tools/train_RetinaNet.py:242-245).  Unlike the reference it does
     not swallow a failing batch (apis/test.py:122-128 would silently misalign image indices)."""
-    if cfg.uncertainty_pool != "Entropy_NMS":
-        raise NotImplementedError(f"uncertainty_pool={cfg.uncertainty_pool!r}: only Entropy_NMS is taken over")
+    if cfg.uncertainty_pool == "Random":     # Uncertainty_fns.Random (apis/test.py:20-25)
+        return torch.randperm(len(data_loader.dataset)).numpy()
+    if cfg.uncertainty_pool not in ("Entropy_NMS", "Entropy_ALL"):     # apis/test.py:27-38, 52-63: one loop for both
+        raise NotImplementedError(f"uncertainty_pool={cfg.uncertainty_pool!r}: Entropy_NMS / Entropy_ALL / Random")
     if "scaleUnc" not in kwargs:
         raise KeyError("scaleUnc")          # the reference reads kwargs['scaleUnc'] unconditionally (:129)
     model.eval()

@@ -91,3 +91,56 @@ def update_X_L(uncertainty, X_all, X_L, X_S_size, device="cuda:0", **kwargs):
     X_L_next.sort()
     X_U_next.sort()
     return X_L_next, X_U_next
+
+
+# ---------------------------------------------------------------------------------------------
+# On-disk formats of the active-learning cycle (the caller side of the path)
+# ---------------------------------------------------------------------------------------------
+def save_cycle(work_dir: str, cycle: int, X_L, X_U, uncertainty) -> None:
+    """What tools/train_RetinaNet.py:249-251 writes after scoring cycle `cycle`: the next cycle's
+    labelled / unlabelled index sets and the score vector, as plain .npy files named
+    X_L_{cycle+1}.npy, X_U_{cycle+1}.npy, Unc_{cycle+1}.npy (dtype and shape as returned by
+    update_X_L / calculate_uncertainty: int64 index arrays, float32[N_all])."""
+    if torch.is_tensor(uncertainty):
+        uncertainty = uncertainty.detach().cpu().numpy()
+    elif not isinstance(uncertainty, np.ndarray):
+        uncertainty = torch.stack(list(uncertainty)).numpy()        # list of 0-d tensors (:242-245)
+    np.save(f"{work_dir}/X_L_{cycle + 1}.npy", np.asarray(X_L))
+    np.save(f"{work_dir}/X_U_{cycle + 1}.npy", np.asarray(X_U))
+    np.save(f"{work_dir}/Unc_{cycle + 1}.npy", uncertainty)
+
+
+def ResumeCycle_WorkDir(work_dir: str, currentCycle: int, fromStartCycle: int):
+    """mmdet/utils/functions.py:485-490: (X_L, X_U) saved for `fromStartCycle`, or (False, False)
+    while the loop is still before that cycle."""
+    if currentCycle < fromStartCycle:
+        return (False, False)
+    return (np.load(f"{work_dir}/X_L_{fromStartCycle}.npy"), np.load(f"{work_dir}/X_U_{fromStartCycle}.npy"))
+
+
+def ResumeCycle(cfg, currentCycle: int, fromStartCycle: int):
+    """mmdet/utils/functions.py:478-483 (same, work_dir taken from the config)."""
+    return ResumeCycle_WorkDir(cfg.work_dir, currentCycle, fromStartCycle)
+
+
+def scoring_stage(cfg, poolModel, data_loader, X_all, X_L, cycle: int, *, zeroRate=0.15, useMaxConf="False",
+                  saveMaxConf=False, clsW=False, scaleUnc=False, score_thr=0.3, iou_thr=0.9, save=True,
+                  calculate=None):
+    """The scoring stage of one AL cycle exactly as the training scripts run it
+    (tools/train_RetinaNet.py:231-251): calculate_uncertainty over the pool loader -> update_X_L ->
+    X_L / X_U / Unc .npy files.  Returns (X_L_next, X_U_next, uncertainty ndarray)."""
+    if calculate is None:
+        from .dropin import calculate_uncertainty as calculate
+    with torch.no_grad():
+        out = calculate(cfg, poolModel, data_loader, return_box=False, showNMS=False, saveUnc=False,
+                        saveMaxConf=saveMaxConf, clsW=clsW, scaleUnc=scaleUnc, score_thr=score_thr, iou_thr=iou_thr)
+    maxconf, uncertainty = (out[1], out[0]) if saveMaxConf else (None, out)
+    if torch.is_tensor(uncertainty):
+        uncertainty = uncertainty.numpy()
+    elif not isinstance(uncertainty, np.ndarray):
+        uncertainty = torch.stack(uncertainty).numpy()
+    X_L_next, X_U_next = update_X_L(uncertainty, X_all, X_L, cfg.X_S_size, zeroRate=zeroRate, maxconf=maxconf,
+                                    useMaxConf=useMaxConf)
+    if save:
+        save_cycle(cfg.work_dir, cycle, X_L_next, X_U_next, uncertainty)
+    return X_L_next, X_U_next, uncertainty

@@ -70,6 +70,7 @@ class BatchResult:
     lam_mean: torch.Tensor
     pair_unc: torch.Tensor
     image_scores: torch.Tensor
+    level_maxconf: torch.Tensor
 
 
 class Scorer:
@@ -112,10 +113,11 @@ class Scorer:
             pair_row=torch.zeros(B, P, **i32), pair_obj=torch.zeros(B, P, **i32),
             pair_cls=torch.zeros(B, P, **i32), pair_off=torch.zeros(B, S + 1, **i32),
             lam_mean=torch.zeros(B, S, **f32), pair_unc=torch.zeros(B, P, 3, **f32),
-            image_scores=torch.zeros(B, **f32))
+            image_scores=torch.zeros(B, **f32), level_maxconf=torch.zeros(B, S, **f32))
         self.bufs = _lib.Buffers()
         for name in _lib.BUFFER_FIELDS:
             setattr(self.bufs, name, self.t[name].data_ptr())
+        self.bufs.level_maxconf = None          # optional output, off unless save_max_conf(True)
         self.ws_bytes = int(self.lib.mehhua_workspace_bytes(C.byref(self.cfg), self._shape_levels, B))
         if self.ws_bytes == 0:
             _lib.check(_lib.E_ARG, "mehhua_workspace_bytes")
@@ -126,6 +128,11 @@ class Scorer:
         self._img_shapes = None
         self._scale_factors = None
         self._ids = None
+
+    def save_max_conf(self, on: bool = True) -> None:
+        """Ask the logits pass to also produce getMaxConf's per-level maxima (utils/functions.py:467-476;
+        the reference computes them only under saveMaxConf).  Off by default."""
+        self.bufs.level_maxconf = self.t["level_maxconf"].data_ptr() if on else None
 
     # ------------------------------------------------------------------ inputs
     def _stream(self) -> int:

@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--e2e-batch", type=int, default=32, help="images per host-buffer call")
     ap.add_argument("--cpu-images", type=int, default=4, help="images of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-gpu-images", type=int, default=0,
+                    help="also time the oracle port in torch-eager on the GPU over this many images (0 = off)")
     return ap.parse_args()
 
 
@@ -131,6 +133,29 @@ def cpu_reference_rate(spec, params, n_images: int, batch: int, threads: int, se
     t0 = time.perf_counter()
     for b in batches:
         O.score_batch(b, **kw)
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def eager_gpu_rate(spec, params, n_images: int, batch: int, device, seed0: int = 20):
+    """the same oracle port run in torch-eager ON the B200 (stock ATen / torchvision
+    kernels) - the 'existing kernels on Blackwell' bar.  Part of the cpu_baseline leg; off by default."""
+    from aod_meh_hua_b200.synth import SyntheticPool
+    from oracle import meh_hua_oracle as O
+    pool = SyntheticPool(spec, seed0=seed0, device="cpu")
+    kw = O.spec_kwargs(spec, params)
+
+    def to_dev(bt):
+        return {k: ([t.to(device) for t in v] if isinstance(v, list) and v and torch.is_tensor(v[0]) else v)
+                for k, v in bt.items()}
+    batches = [to_dev(pool.batch(list(range(i, min(i + batch, n_images))))) for i in range(0, n_images, batch)]
+    torch.manual_seed(20)
+    O.score_batch(to_dev(pool.batch([n_images, n_images + 1])), **kw)      # warm-up (not timed)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for bt in batches:
+        O.score_batch(bt, **kw)
+    torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
     return n_images / dt, dt
 
@@ -372,6 +397,14 @@ def main():
         cpu_baseline = dict(value=rate, unit=UNIT, cores=cores, kind="port",
                             sample=f"{args.cpu_images} images of {spec.name}, batch 2, T={params.n_samples}, "
                                    f"oracle port on torch CPU, {dt:.1f} s")
+        if args.eager_gpu_images > 0:
+            try:
+                r2, dt2 = eager_gpu_rate(spec, params, args.eager_gpu_images, 2, device)
+                cpu_baseline["torch_eager_b200"] = dict(
+                    value=r2, unit=UNIT, sample=f"{args.eager_gpu_images} images, batch 2, T={params.n_samples}, oracle "
+                                                f"port in torch-eager on cuda (ATen / torchvision kernels), {dt2:.1f} s")
+            except Exception as e:      # a reported side baseline: never fails the bench line
+                cpu_baseline["torch_eager_b200"] = dict(error=f"{type(e).__name__}: {e}"[:200])
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic",

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MEHHUA_ABI_VERSION 1
+#define MEHHUA_ABI_VERSION 2
 #define MEHHUA_MAX_LEVELS 8
 #define MEHHUA_MAX_DETS 256      /* upper bound on max_per_img */
 #define MEHHUA_MAX_NMS_PRE 4096  /* upper bound on nms_pre */
@@ -118,6 +118,9 @@ typedef struct mehhua_buffers {
   float*   lam_mean;     /* [B, S]             mean lambda over the level's pairs                 */
   float*   pair_unc;     /* [B, pair_cap, 3]   total, aleatoric, epistemic (Lambda_L2.py:521-525) */
   float*   image_scores; /* [B]                AggregateObjScaleUnc output                        */
+  float*   level_maxconf;/* [B, S] or NULL     max over ALL priors of max_c softmax: the `output`   *
+                          *                    of getMaxConf (utils/functions.py:467-476); fused   *
+                          *                    into the logits pass (K1a / KA1), NULL = skipped     */
 } mehhua_buffers_t;
 
 int         mehhua_abi_version(void);

@@ -217,18 +217,35 @@ def kat_goldens():
     np.random.seed(11)
     xl2, xu2 = ns["update_X_L"](unc.copy(), X_all, X_L.copy(), 80)
     g["sel2_X_L_next"], g["sel2_X_U_next"] = xl2, xu2
+    # update_X_L with the zero-score picks taken by max confidence (useMaxConf 'min' / 'max', :113-119)
+    maxconf = rs.rand(n).astype(np.float32)
+    g["sel_maxconf"] = maxconf
+    for mode in ("min", "max"):
+        np.random.seed(11)
+        xl3, xu3 = ns["update_X_L"](unc.copy(), X_all, X_L.copy(), 80, zeroRate=0.15, maxconf=maxconf.tolist(),
+                                    useMaxConf=mode)
+        g[f"sel_{mode}_X_L_next"], g[f"sel_{mode}_X_U_next"] = xl3, xu3
+    # getMaxConf (utils/functions.py:467-476) on the tiny batches
+    RL.load_functions("mmdet/utils/functions.py", ["getMaxConf"], ns)
+    for spec_name in ("tiny_retina_coco", "tiny_ssd_voc"):
+        spec = get_spec(spec_name)
+        batch = SyntheticPool(spec, seed0=20).batch([0, 1, 2])
+        per_img, per_level = ns["getMaxConf"](batch["cls_scores"], spec.c_out)
+        g[f"maxconf_{spec_name}"] = np.asarray(per_img, dtype=np.float64)
+        g[f"maxconf_levels_{spec_name}"] = per_level.numpy()
     return g
 
 
 def main():
     assert RL.available(), "reference tree not mounted"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name, spec_name, gids, pseed, sseed, sf, up2, clsw in CASES:
+    only_kats = "--only-kats" in sys.argv
+    for name, spec_name, gids, pseed, sseed, sf, up2, clsw in ([] if only_kats else CASES):
         g = run_reference_case(spec_name, gids, pseed, sseed, sf, up2, clsw)
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")
-    for name, spec_name, gids, pseed, sseed, kind in ALL_CASES:
+    for name, spec_name, gids, pseed, sseed, kind in ([] if only_kats else ALL_CASES):
         g = run_reference_all_case(spec_name, gids, pseed, sseed, kind)
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)

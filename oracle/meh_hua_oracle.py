@@ -172,8 +172,12 @@ def multiclass_nms(boxes: torch.Tensor, scores: torch.Tensor, score_thr: float, 
     max_coord = cb.max()
     off = lab.to(cb) * (max_coord + torch.tensor(1).to(cb))
     shifted = cb + off[:, None]
-    keep = greedy_nms(shifted.numpy(), cs.numpy(), iou_thr, max_num)
-    keep_t = torch.from_numpy(keep)
+    if cb.is_cuda:      # torch-eager-on-GPU baseline only: torchvision's stock CUDA NMS (same rule)
+        from torchvision.ops import nms as tv_nms
+        keep_t = tv_nms(shifted, cs, iou_thr)
+    else:
+        keep = greedy_nms(shifted.numpy(), cs.numpy(), iou_thr, max_num)
+        keep_t = torch.from_numpy(keep)
     dets = torch.cat([cb[keep_t], cs[keep_t][:, None]], -1)
     if max_num > 0:
         dets, keep_t = dets[:max_num], keep_t[:max_num]
@@ -206,10 +210,10 @@ def pre_stage(cls_scores: List[torch.Tensor], bbox_preds: List[torch.Tensor],
             _, idx = topk_keys(sc, head).topk(k)
             if topk_override is not None:
                 idx = topk_override[lv].long()
-            bi = torch.arange(B).view(-1, 1).expand_as(idx)
+            bi = torch.arange(B, device=idx.device).view(-1, 1).expand_as(idx)
             an, dl, sc, lm = an[bi, idx, :], dl[bi, idx, :], sc[bi, idx, :], lm[bi, idx]
         else:
-            idx = torch.arange(n).view(1, -1).expand(B, n)
+            idx = torch.arange(n, device=sc.device).view(1, -1).expand(B, n)
         lvl_boxes.append(delta2bbox(an, dl, stds, max_shape=img_shapes))
         lvl_scores.append(sc)
         lvl_L.append(lm)
@@ -298,9 +302,10 @@ def compute_obj_unc(cls_scores: List[torch.Tensor], pos_bboxes: List[torch.Tenso
                 for c in ps[om].argmax(dim=1).unique():
                     m = om & (pcls == c)
                     nested[i][obj][s][f"{c}"] = (ale[m].mean(), epi[m].mean())
-            flat.append(dict(image=i, level=s, row=(pidx + start).numpy(), obj=oidx.numpy(),
-                             cls=pcls.numpy(), lam_p=lam_p.numpy(), alpha=alpha.numpy(),
-                             total=total.numpy(), ale=ale.numpy(), epi=epi.numpy()))
+            if not ps.is_cuda:       # stage records for the parity tests (skipped by the eager-GPU baseline)
+                flat.append(dict(image=i, level=s, row=(pidx + start).numpy(), obj=oidx.numpy(),
+                                 cls=pcls.numpy(), lam_p=lam_p.numpy(), alpha=alpha.numpy(),
+                                 total=total.numpy(), ale=ale.numpy(), epi=epi.numpy()))
         start = end
     return nested, flat, level_fg
 
@@ -440,6 +445,18 @@ def spec_kwargs(spec, params=None) -> Dict[str, object]:
 # --------------------------------------------------------------------------------------------
 # closed forms for moment matching of a free-running sampler (SURVEY 7 "Sampling parity")
 # --------------------------------------------------------------------------------------------
+def get_max_conf(cls_scores: List[torch.Tensor], n_cls: int):
+    """getMaxConf (mmdet/utils/functions.py:467-476): per (image, level) the largest softmax
+    probability over all priors and ALL classes (background included for SSD), and its maximum over
+    levels.  Returns (list[float] per image, Tensor[B, S])."""
+    B = cls_scores[0].size(0)
+    out = torch.zeros(B, len(cls_scores), device=cls_scores[0].device)
+    for s, x in enumerate(cls_scores):
+        p = x.permute(0, 2, 3, 1).reshape(B, -1, n_cls).softmax(dim=-1)
+        out[:, s] = p.reshape(B, -1).max(dim=-1)[0]
+    return out.max(dim=-1)[0].tolist(), out
+
+
 def dirichlet_expectations(alpha: np.ndarray):
     """alpha [P,C] (float64) -> (H(mean), E[entropy], epistemic_inf) per row:
     mean = alpha/alpha0; E[-sum x ln x] = psi(alpha0+1) - sum mean_c psi(alpha_c+1)."""

@@ -278,3 +278,100 @@ def test_ablation_variant_parameters():
     _, unc = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, L_scores=lam, **kw)
     want = run_oracle(spec, batch, ScoringParams(fg_thr=0.2, obj_thr=0.2, cluster_iou=0.4, use_lambda=False))[0]["image_scores"]
     np.testing.assert_allclose(unc, want, rtol=0.15, atol=0.05)
+
+
+@pytest.mark.parametrize("spec_name", ["tiny_retina_coco", "tiny_ssd_voc", "tiny_retina_c12", "tiny_ssd_c7"])
+def test_max_conf_fused_into_the_logits_pass(spec_name):
+    """getMaxConf (utils/functions.py:467-476): level maxima come out of K1a (Entropy_NMS) and KA1
+    (Entropy_ALL); golden = the reference function's own output, generic class counts vs the oracle."""
+    import os
+    from aod_meh_hua_b200.dropin import max_conf
+    from aod_meh_hua_b200.scoring import Scorer
+    spec, batch = make_batch(spec_name, [0, 1, 2])
+    want_img, want_lvl = O.get_max_conf(batch["cls_scores"], spec.c_out)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kats.npz"))
+    if f"maxconf_levels_{spec_name}" in g.files:
+        assert np.array_equal(want_lvl.numpy(), g[f"maxconf_levels_{spec_name}"])
+        want_lvl = torch.from_numpy(g[f"maxconf_levels_{spec_name}"])
+    for mode, agg in (("nms", "objectSum_scaleMax_classSum"), ("all", "scaleSum_classSum")):
+        sc = Scorer(spec, ScoringParams(n_samples=8, agg=agg), max_batch=3, mode=mode)
+        with pytest.raises(_lib.MehhuaError):
+            max_conf(sc)
+        sc.save_max_conf(True)
+        sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                 batch["scale_factors"])
+        per_img, per_lvl = max_conf(sc)
+        np.testing.assert_allclose(per_lvl.cpu().numpy(), want_lvl.numpy(), rtol=1e-5)
+        np.testing.assert_allclose(per_img, want_lvl.max(dim=1)[0].numpy(), rtol=1e-5)
+    # the head method returns it as the third item when saveMaxConf is set (Lambda_L2.py:376-381)
+    head = _head(spec)
+    cls, reg, lam, anc = _cuda(batch)
+    sf = [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]]
+    kw = dict(KW, saveMaxConf=True)
+    r = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, True, L_scores=lam, **kw)
+    assert len(r) == 3 and isinstance(r[2], list) and len(r[2]) == 3
+    np.testing.assert_allclose(r[2], want_img, rtol=1e-5)
+    kw_all = dict(kw, uPool="Entropy_ALL", uPool2="scaleAvg_classAvg")
+    r = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam, **kw_all)
+    assert len(r) == 3
+    np.testing.assert_allclose(r[2], want_img, rtol=1e-5)
+
+
+def test_update_X_L_max_conf_modes_match_the_reference():
+    """useMaxConf 'min' / 'max' (active_datasets.py:113-119) against the reference's own outputs."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kats.npz"))
+    unc, X_L, maxconf = g["sel_unc"], g["sel_X_L"], g["sel_maxconf"]
+    X_all = np.arange(len(unc))
+    # the golden pool has tied zero scores only below the selected range: the top part is tie-free
+    for mode in ("min", "max"):
+        np.random.seed(11)
+        xl, xu = update_X_L(unc.copy(), X_all, X_L.copy(), 80, zeroRate=0.15, maxconf=maxconf.tolist(), useMaxConf=mode)
+        assert np.array_equal(xl, g[f"sel_{mode}_X_L_next"]) and np.array_equal(xu, g[f"sel_{mode}_X_U_next"])
+    np.random.seed(11)
+    xl, xu = update_X_L(unc.copy(), X_all, X_L.copy(), 80, zeroRate=0.15, maxconf=None, useMaxConf="False")
+    assert np.array_equal(xl, g["sel_X_L_next"]) and np.array_equal(xu, g["sel_X_U_next"])
+
+
+def test_scoring_stage_writes_the_cycle_files(tmp_path):
+    """tools/train_RetinaNet.py:231-251: calculate_uncertainty -> update_X_L -> X_L/X_U/Unc .npy,
+    readable back through ResumeCycle; Entropy_ALL and Random pools use the same loop."""
+    from aod_meh_hua_b200.dropin import ResumeCycle, scoring_stage
+    spec, batch = make_batch("tiny_retina_coco", [0, 1, 2, 3, 4, 5])
+    head = _head(spec)
+    cls, reg, lam, anc = _cuda(batch)
+    sf = [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]]
+
+    class Model:
+        def eval(self):
+            return self
+
+        def __call__(self, return_loss, rescale, isEval, batchIdx, img, img_metas, **kw):
+            lo = batchIdx * 2
+            return head._get_bboxes([c[lo:lo + 2] for c in cls], [c[lo:lo + 2] for c in reg], anc,
+                                    batch["img_shapes"][lo:lo + 2], sf[lo:lo + 2], None, rescale,
+                                    kw.get("uPool") != "Entropy_ALL", L_scores=[c[lo:lo + 2] for c in lam],
+                                    isEval=isEval, batchIdx=batchIdx, **kw)
+
+    class Loader(list):
+        dataset = list(range(6))
+
+    loader = Loader(dict(img=torch.zeros(2), img_metas=[{}, {}]) for _ in range(3))
+    X_all, X_L = np.arange(6), np.array([1])
+    for pool, up2, smc in (("Entropy_NMS", "objectSum_scaleMax_classSum", False),
+                           ("Entropy_NMS", "objectSum_scaleMax_classSum", True),
+                           ("Entropy_ALL", "scaleSum_classSum", False)):
+        cfg = _Cfg(uncertainty_pool=pool, uncertainty_type="Epistemic", uncertainty_pool2=up2, X_S_size=2,
+                   work_dir=str(tmp_path))
+        np.random.seed(5)
+        xl, xu, unc = scoring_stage(cfg, Model(), loader, X_all, X_L, cycle=0, saveMaxConf=smc,
+                                    useMaxConf="min" if smc else "False")
+        assert unc.dtype == np.float32 and unc.shape == (6,) and np.all(unc >= 0)
+        assert len(xl) == 3 and 1 in xl and np.all(np.diff(xl) > 0)
+        rl, ru = ResumeCycle(cfg, 1, 1)
+        assert np.array_equal(rl, xl) and np.array_equal(ru, xu)
+        assert np.array_equal(np.load(tmp_path / "Unc_1.npy"), unc)
+        assert ResumeCycle(cfg, 0, 1) == (False, False)
+    cfg = _Cfg(uncertainty_pool="Random", uncertainty_type="Epistemic", uncertainty_pool2="x", X_S_size=2, work_dir=str(tmp_path))
+    perm = calculate_uncertainty(cfg, Model(), loader, scaleUnc=False)
+    assert sorted(perm.tolist()) == list(range(6))

@@ -147,3 +147,36 @@ def test_parse_agg_spec_tokens():
     assert parse_agg_spec("classAvg_objectMax_scaleSum") == (2, 0, 1)
     with pytest.raises(KeyError):
         parse_agg_spec("objectMin_scaleMax_classSum")
+
+
+def test_cycle_files_round_trip(tmp_path):
+    """X_L_k / X_U_k / Unc_k .npy (tools/train_RetinaNet.py:249-251) and ResumeCycle
+    (utils/functions.py:478-490)."""
+    import types
+    from aod_meh_hua_b200.pool import ResumeCycle, ResumeCycle_WorkDir, save_cycle
+    X_L, X_U = np.array([1, 5, 9]), np.array([0, 2, 3])
+    unc = [torch.tensor(float(i)) for i in range(10)]           # the list of 0-d tensors the scorer returns
+    save_cycle(str(tmp_path), 3, X_L, X_U, unc)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["Unc_4.npy", "X_L_4.npy", "X_U_4.npy"]
+    u = np.load(tmp_path / "Unc_4.npy")
+    assert u.dtype == np.float32 and u.shape == (10,)
+    cfg = types.SimpleNamespace(work_dir=str(tmp_path))
+    assert ResumeCycle(cfg, 3, 4) == (False, False)
+    rl, ru = ResumeCycle(cfg, 4, 4)
+    assert np.array_equal(rl, X_L) and np.array_equal(ru, X_U) and rl.dtype == X_L.dtype
+    rl2, _ = ResumeCycle_WorkDir(str(tmp_path), 6, 4)
+    assert np.array_equal(rl2, X_L)
+
+
+def test_oracle_max_conf_matches_reference():
+    import os
+    from aod_meh_hua_b200.specs import get_spec
+    from aod_meh_hua_b200.synth import SyntheticPool
+    from oracle import meh_hua_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kats.npz"))
+    for name in ("tiny_retina_coco", "tiny_ssd_voc"):
+        spec = get_spec(name)
+        batch = SyntheticPool(spec, seed0=20).batch([0, 1, 2])
+        per_img, per_lvl = O.get_max_conf(batch["cls_scores"], spec.c_out)
+        assert np.array_equal(per_lvl.numpy(), g[f"maxconf_levels_{name}"])
+        assert np.array_equal(np.asarray(per_img, dtype=np.float64), g[f"maxconf_{name}"])
