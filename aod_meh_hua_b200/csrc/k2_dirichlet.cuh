@@ -14,10 +14,14 @@
 // nor need special casing; the reference's FLT_MIN clamp only changes terms below 1e-36.
 // Randomness: counter-based Philox4x32-10 keyed by the seed, counter = (sample, call index, pair
 // identity (row, object), global image id) - independent of batch composition and world size.
-// Layout: one warp owns a pair; lane = sample (32 at a time).  ln g of the warp's 32 samples sits
-// in shared memory as lbuf[class][lane] (row stride 33: conflict-free both for the lane-private
-// accesses of the draw / normalise passes and for the transposed class-sum pass).  Samples never
-// touch global memory.
+// Layout: one warp owns a pair; lane = sample (32 at a time).  The scaled draws e_c = g_c / 2^m of
+// the warp's 32 samples sit in shared memory as lbuf[class][lane] in bfloat16 (round-to-nearest;
+// row stride 34 halves = 17 words: conflict-free both for the lane-private stores of the draw loop
+// and for the transposed class-sum pass).  Only the class means are formed from the bf16 copies
+// (relative rounding error 2^-9 per term, unbiased, averaged over T samples - two orders below the
+// Monte-Carlo error of the estimator); the per-sample sum A and the entropy terms stay in fp32
+// registers.  Half-width rows are what lets three blocks (24 warps) share an SM.  Samples never touch
+// global memory.
 #pragma once
 #include "common.cuh"
 
@@ -25,7 +29,7 @@ namespace mehhua {
 
 constexpr int kK2Threads = 256;
 constexpr int kK2Warps = kK2Threads / 32;
-constexpr int kLStride = 33;
+constexpr int kLStride = 34;                          // bf16 elements per class row (17 words)
 constexpr float kFltMin = 1.17549435e-38f;
 constexpr float kInvE = 0.36787944117144233f;
 constexpr float kTwoM32 = 2.3283064365386963e-10f;   // 2^-32
@@ -53,12 +57,15 @@ __device__ __forceinline__ float4 lds_v4(unsigned a) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void sts_bf16(unsigned a, float v) {      // round-to-nearest-even fp32 -> bf16
+  asm volatile("{ .reg .b16 h; cvt.rn.bf16.f32 h, %1; st.shared.b16 [%0], h; }" :: "r"(a), "f"(v));
+}
 __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // per-warp shared memory, in floats:
-//   cst4[C] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*33] | alpha[C] | avg[C] | lists 3 x C bytes
+//   cst4[C] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*17 words] | alpha[C] | avg[C] | lists 3 x C bytes
 __host__ __device__ inline size_t k2_warp_floats(int C) {
-  const size_t f = 4 * (size_t)C + (size_t)C * kLStride + 2 * (size_t)C + (3 * (size_t)C + 3) / 4;
+  const size_t f = 4 * (size_t)C + (size_t)C * (kLStride / 2) + 2 * (size_t)C + (3 * (size_t)C + 3) / 4;
   return (f + 3) & ~(size_t)3;
 }
 __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_warp_floats(C) * sizeof(float) + 1040 * sizeof(int); }
@@ -99,7 +106,7 @@ __device__ __forceinline__ void split_block(const uint4 w, float (&f0)[3], float
   f1[2] = __uint_as_float(0x3f800000u | ((w.w << 1) & 0x7ffff8u));                         // w.w[21:2]
 }
 
-__global__ void __launch_bounds__(kK2Threads, 2)
+__global__ void __launch_bounds__(kK2Threads, 3)
 k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ score_rows,
                     const float* __restrict__ lam_rows, const float* __restrict__ lam_mean,
                     const int* __restrict__ pair_row, const int* __restrict__ pair_obj,
@@ -112,8 +119,8 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
   float* wbase = reinterpret_cast<float*>(img_pref + 1040) + (size_t)(threadIdx.x >> 5) * k2_warp_floats(C);
   float4* cst4 = reinterpret_cast<float4*>(wbase);            // [C]
-  float* lbuf = wbase + 4 * C;                                // [C][33], log2 units
-  float* s_alpha = lbuf + C * kLStride;                       // [C]
+  unsigned* lbuf = reinterpret_cast<unsigned*>(wbase + 4 * C);   // [C][17 words] = [C][34] bf16
+  float* s_alpha = wbase + 4 * C + C * (kLStride / 2);        // [C]
   float* s_avg = s_alpha + C;                                 // [C]
   unsigned char* s_small = reinterpret_cast<unsigned char*>(s_avg + C);
   unsigned char* s_big = s_small + C;
@@ -121,7 +128,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   const int lane = threadIdx.x & 31;
   const unsigned a_cst4 = (unsigned)__cvta_generic_to_shared(cst4);
   const unsigned a_small = (unsigned)__cvta_generic_to_shared(s_small);
-  const unsigned a_lrow = (unsigned)__cvta_generic_to_shared(lbuf) + 4u * lane;   // my column of row 0
+  const unsigned a_lrow = (unsigned)__cvta_generic_to_shared(lbuf) + 2u * lane;   // my column of row 0
 
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -156,6 +163,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
     __syncwarp();
     // class lists: big (alpha >= 1), small (0 < alpha < 1), bad (alpha <= 0, denormal-tiny or non-finite)
     int nsmall = 0, nbig = 0, nbad = 0;
+    float amax = 0.f;
     for (int c0 = 0; c0 < C; c0 += 32) {
       const int c = c0 + lane;
       float a = 0.f;
@@ -165,7 +173,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       const bool big = valid && !bad && a >= 1.f;
       const bool small = valid && !bad && a < 1.f;
       const unsigned mb = __ballot_sync(full, big), ms = __ballot_sync(full, small), mx = __ballot_sync(full, bad);
-      if (big) s_big[nbig + __popc(mb & lt_mask)] = (unsigned char)c;
+      if (big) { s_big[nbig + __popc(mb & lt_mask)] = (unsigned char)c; amax = fmaxf(amax, a); }
       if (small) {      // list entry = class id; the GS constants sit at the same list position
         const int pos = nsmall + __popc(ms & lt_mask);
         const float bb = fmaf(a, kInvE, 1.f);
@@ -179,6 +187,9 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         s_avg[c] = 0.f;
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
+    const float m = nbig > 0 ? lg2_approx(amax) : 0.f;     // reference exponent of the scaled draws
     if (nbad > 0 && lane == 0) atomicOr(status, MEHHUA_ST_BAD_ALPHA);
     __syncwarp();
 
@@ -208,17 +219,17 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       for (int t0 = 0; t0 < T; t0 += 32) {
         const int t = t0 + lane;
         const bool active = t < T;
-        // Normalisation is a log-sum-exp around a reference exponent m fixed BEFORE the bulk of the
-        // draws: the largest of the alpha >= 1 draws (they own the sample; 0 when there are none).
+        // Normalisation is a log-sum-exp around a reference exponent m fixed BEFORE the draws:
+        // log2 of the largest alpha when some alpha >= 1 (its draw owns the sample and is within a
+        // few octaves of alpha), 0 otherwise.
         //   e_c = 2^(l_c - m),  A = sum_c e_c,  x_c = e_c / A,
         //   -sum_c x ln x = ln A - ln2 * (sum_c e_c d_c) / A   with d_c = l_c - m (log2 units)
         // Any m gives the same value; fixing it early lets every accepted draw be folded into A and
         // the entropy sum on the spot, so the draws are stored as e_c and read back only once.
-        float m = 0.f, asum = 0.f, bs = 0.f;
+        float asum = 0.f, bs = 0.f;
         if (active) {
-          for (int i = 0; i < nbad; ++i) lbuf[s_bad[i] * kLStride + lane] = 0.f;
+          for (int i = 0; i < nbad; ++i) sts_bf16(a_lrow + s_bad[i] * (kLStride * 2u), 0.f);
           // Marsaglia-Tsang for the few classes with alpha >= 1
-          float mbig = -INFINITY;
           for (int i = 0; i < nbig; ++i) {
             const int c = s_big[i];
             const float d = s_alpha[c] - (1.f / 3.f);
@@ -235,21 +246,15 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
                 if (kLn2 * lg2_approx(u24(w.z)) < fmaf(d, fmaf(kLn2, lv2, 1.f - v), 0.5f * x * x)) { l2 = lg2_approx(d) + lv2; break; }
               }
             }
-            lbuf[c * kLStride + lane] = l2;
-            mbig = fmaxf(mbig, l2);
-          }
-          if (nbig > 0) m = mbig;
-          for (int i = 0; i < nbig; ++i) {
-            const int c = s_big[i];
-            const float d = lbuf[c * kLStride + lane] - m;
-            const float e = ex2_approx(d);
+            const float dl = l2 - m;
+            const float e = ex2_approx(dl);
             asum += e;
-            bs = fmaf(e, d, bs);
-            lbuf[c * kLStride + lane] = e;
+            bs = fmaf(e, dl, bs);
+            sts_bf16(a_lrow + c * (kLStride * 2u), e);
           }
         } else {
           unsigned addr = a_lrow;
-          for (int c = 0; c < C; ++c, addr += kLStride * 4u) sts_f32(addr, 0.f);
+          for (int c = 0; c < C; ++c, addr += kLStride * 2u) sts_bf16(addr, 0.f);
         }
         // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with three cursors (list positions
         // mod 3): each iteration one Philox block (128 bits = 3 x (22 + 20)) feeds one attempt per
@@ -267,9 +272,9 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
             const bool okc = gs_attempt(ic, nsmall, f0[2], f1[2], a_small, a_cst4, cc, lc);
             const float da = fmaxf(la - m, -300.f), db = fmaxf(lb - m, -300.f), dc = fmaxf(lc - m, -300.f);
             const float ea = ex2_approx(da), eb = ex2_approx(db), ec = ex2_approx(dc);
-            if (oka) { sts_f32(a_lrow + ca * (kLStride * 4u), ea); asum += ea; bs = fmaf(ea, da, bs); ia += 3; }
-            if (okb) { sts_f32(a_lrow + cb * (kLStride * 4u), eb); asum += eb; bs = fmaf(eb, db, bs); ib += 3; }
-            if (okc) { sts_f32(a_lrow + cc * (kLStride * 4u), ec); asum += ec; bs = fmaf(ec, dc, bs); ic += 3; }
+            if (oka) { sts_bf16(a_lrow + ca * (kLStride * 2u), ea); asum += ea; bs = fmaf(ea, da, bs); ia += 3; }
+            if (okb) { sts_bf16(a_lrow + cb * (kLStride * 2u), eb); asum += eb; bs = fmaf(eb, db, bs); ib += 3; }
+            if (okc) { sts_bf16(a_lrow + cc * (kLStride * 2u), ec); asum += ec; bs = fmaf(ec, dc, bs); ic += 3; }
           }
         }
         float inv_a = 0.f;
@@ -278,22 +283,25 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
           ent_acc += logf(asum) - kLn2 * bs * inv_a;
         }
         __syncwarp();
-        // class sums over the 32 samples, transposed: lane = class, walk the samples
+        // class sums over the 32 samples, transposed: lane = class, walk the samples two at a time
+        // (one word = the bf16 copies of samples 2w and 2w+1; bf16 -> fp32 is a shift / a mask)
         for (int c0 = 0; c0 < C; c0 += 128) {
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
           const int c = c0 + lane;
-          const float* r0p = lbuf + (size_t)min(c, C - 1) * kLStride;
-          const float* r1p = lbuf + (size_t)min(c + 32, C - 1) * kLStride;
-          const float* r2p = lbuf + (size_t)min(c + 64, C - 1) * kLStride;
-          const float* r3p = lbuf + (size_t)min(c + 96, C - 1) * kLStride;
+          const unsigned* r0p = lbuf + (size_t)min(c, C - 1) * (kLStride / 2);
+          const unsigned* r1p = lbuf + (size_t)min(c + 32, C - 1) * (kLStride / 2);
+          const unsigned* r2p = lbuf + (size_t)min(c + 64, C - 1) * (kLStride / 2);
+          const unsigned* r3p = lbuf + (size_t)min(c + 96, C - 1) * (kLStride / 2);
           const int rem = C - c0;
-#pragma unroll 8
-          for (int tt = 0; tt < 32; ++tt) {
-            const float iv = __shfl_sync(full, inv_a, tt);
-            a0 = fmaf(r0p[tt], iv, a0);
-            if (rem > 32) a1 = fmaf(r1p[tt], iv, a1);
-            if (rem > 64) a2 = fmaf(r2p[tt], iv, a2);
-            if (rem > 96) a3 = fmaf(r3p[tt], iv, a3);
+#pragma unroll 4
+          for (int w = 0; w < 16; ++w) {
+            const float iv0 = __shfl_sync(full, inv_a, 2 * w), iv1 = __shfl_sync(full, inv_a, 2 * w + 1);
+            unsigned u = r0p[w];
+            a0 = fmaf(__uint_as_float(u << 16), iv0, a0);
+            a0 = fmaf(__uint_as_float(u & 0xffff0000u), iv1, a0);
+            if (rem > 32) { u = r1p[w]; a1 = fmaf(__uint_as_float(u << 16), iv0, a1); a1 = fmaf(__uint_as_float(u & 0xffff0000u), iv1, a1); }
+            if (rem > 64) { u = r2p[w]; a2 = fmaf(__uint_as_float(u << 16), iv0, a2); a2 = fmaf(__uint_as_float(u & 0xffff0000u), iv1, a2); }
+            if (rem > 96) { u = r3p[w]; a3 = fmaf(__uint_as_float(u << 16), iv0, a3); a3 = fmaf(__uint_as_float(u & 0xffff0000u), iv1, a3); }
           }
           if (c < C) s_avg[c] += a0;
           if (c + 32 < C) s_avg[c + 32] += a1;
