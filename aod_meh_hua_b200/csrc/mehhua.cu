@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -150,11 +152,11 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
 }
 
 int check_device() {
-  static int state = 0;   // 0 unknown, 1 ok, <0 error
-  if (state == 1) return 0;
+  static std::atomic<unsigned long long> ok_mask{0};   // devices (by ordinal < 64) already verified
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return MEHHUA_E_NODEVICE; }
+  if (dev < 64 && (ok_mask.load(std::memory_order_relaxed) >> dev) & 1ull) return 0;
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) { cuda_fail(e, "cudaGetDeviceProperties"); return MEHHUA_E_NODEVICE; }
@@ -162,19 +164,38 @@ int check_device() {
     snprintf(g_err, sizeof(g_err), "mehhua kernels are built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
     return MEHHUA_E_NODEVICE;
   }
-  state = 1;
+  if (dev < 64) ok_mask.fetch_or(1ull << dev, std::memory_order_relaxed);
   return 0;
 }
 
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = (dev >= 0 && dev < 64) ? cached[dev].load(std::memory_order_relaxed) : 0;
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// Opt-in dynamic shared memory is a per-device function attribute: remember, per (device, kernel),
+// the largest size already granted.  Thread-safe; one map lookup per launch.
+template <typename F>
+int ensure_dyn_smem(F* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = granted[{dev, reinterpret_cast<const void*>(kernel)}];
+  if (bytes > cur) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  return 0;
 }
 
 struct Prepared {
@@ -209,11 +230,7 @@ int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes,
   bool any_topk = false;
   for (int s = 0; s < p.S; ++s) any_topk |= p.lv[s].topk != 0;
   if (any_topk) {
-    static bool attr = false;
-    if (!attr) {
-      CU(cudaFuncSetAttribute(k1b_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelSmem));
-      attr = true;
-    }
+    if (int rc = ensure_dyn_smem(k1b_select_kernel, kSelSmem)) return rc;
     k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.inv_map, ws.status);
     LAUNCHED("k1b_select_kernel");
   }
@@ -264,11 +281,7 @@ int launch_all_typed(const Plan& p, const Workspace& ws, const mehhua_buffers_t*
   ka_fg_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
       p, ws.fg_list, ws.fg_cnt, ws.lam_part, ws.status, reinterpret_cast<unsigned*>(o->level_maxconf));
   LAUNCHED("ka_fg_kernel");
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(ka_finalize_kernel<C, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAllSmem));
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(ka_finalize_kernel<C, HEAD>, kAllSmem)) return rc;
   ka_finalize_kernel<C, HEAD><<<p.B, kAllThreads, kAllSmem, st>>>(
       p, ws.fg_list, ws.fg_cnt, ws.lam_part, o->score_rows, o->lam_rows, o->topk_idx, o->row_max, o->row_argmax,
       o->level_fg, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off, o->lam_mean, o->n_obj, o->n_det, ws.status);
@@ -299,11 +312,7 @@ int launch_all(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cu
 int launch_nms(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
   if (!o || !o->boxes || !o->dets || !o->det_labels || !o->det_flat || !o->n_det || !o->n_obj)
     return arg_fail("null NMS buffer");
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k3a_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmem));
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(k3a_nms_kernel, kNmsSmem)) return rc;
   k3a_nms_kernel<<<p.B, kNmsThreads, kNmsSmem, st>>>(p, ws.cand, ws.cand_cnt, ws.cand_maxc, o->boxes, o->dets,
                                                     o->det_labels, o->det_flat, o->n_det, o->n_obj, ws.status);
   LAUNCHED("k3a_nms_kernel");
@@ -314,11 +323,7 @@ int launch_pairs(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, 
   if (!o || !o->boxes || !o->row_max || !o->row_argmax || !o->lam_rows || !o->level_fg || !o->dets || !o->n_obj ||
       !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->lam_mean)
     return arg_fail("null pair buffer");
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k3b_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(k3b_pairs_kernel, kPairSmem)) return rc;
   k3b_pairs_kernel<<<p.B, kPairThreads, kPairSmem, st>>>(p, o->boxes, o->row_max, o->row_argmax, o->lam_rows, o->level_fg,
                                                  o->dets, o->n_obj, o->pair_row, o->pair_obj, o->pair_cls,
                                                  o->pair_off, o->lam_mean, ws.status);
@@ -334,13 +339,20 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
   if (p.C > 256) return arg_fail("c_out must be <= 256 for the K2 class lists");
   const size_t smem = k2_smem_bytes(p.C);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K2 shared-memory layout");
-  static size_t attr = 0;
-  static int blocks_per_sm = 1;
-  if (smem != attr) {
-    CU(cudaFuncSetAttribute(k2_dirichlet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k2_dirichlet_kernel, kK2Threads, smem));
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    attr = smem;
+  if (int rc = ensure_dyn_smem(k2_dirichlet_kernel, smem)) return rc;
+  int blocks_per_sm = 1;
+  {   // resident blocks per SM for this (device, shared-memory size): the persistent grid's width
+    static std::mutex mu;
+    static std::map<std::pair<int, size_t>, int> cache;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int& v = cache[{dev, smem}];
+    if (v == 0) {
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k2_dirichlet_kernel, kK2Threads, smem));
+      if (v < 1) v = 1;
+    }
+    blocks_per_sm = v;
   }
   CU(cudaMemsetAsync(ws.work_counter, 0, sizeof(int), st));
   k2_dirichlet_kernel<<<sm_count() * blocks_per_sm, kK2Threads, smem, st>>>(
@@ -357,11 +369,7 @@ int launch_hua(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cu
     return arg_fail("null HUA buffer");
   const size_t smem = k3c_smem_bytes(p.S, p.C);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K3c shared-memory layout");
-  static size_t attr = 0;
-  if (smem > attr) {
-    CU(cudaFuncSetAttribute(k3c_hua_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  if (int rc = ensure_dyn_smem(k3c_hua_kernel, smem)) return rc;
   k3c_hua_kernel<<<p.B, kHuaThreads, smem, st>>>(p, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off,
                                                 o->pair_unc, o->n_obj, o->image_scores, ws.status);
   LAUNCHED("k3c_hua_kernel");
@@ -537,11 +545,7 @@ int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int
   if (workspace_bytes < 256) return MEHHUA_E_WORKSPACE;
   if (n < 0 || n > 0x7fffffffll || k < 0) return arg_fail("pool size / k");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k4_pool_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolSmem));
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(k4_pool_topk_kernel, kPoolSmem)) return rc;
   k4_pool_topk_kernel<<<1, kPoolThreads, kPoolSmem, st>>>(scores, mask, (long long)n, k,
                                                          reinterpret_cast<long long*>(idx_out), n_selected_out,
                                                          static_cast<unsigned*>(workspace));
