@@ -1,6 +1,8 @@
 """GPU parity: every stage of the CUDA path (through the C ABI) against the CPU oracle on the same
 seeded inputs.  Integer decisions (top-k membership and order, level-FG flags, NMS keep list,
 pair list, class keys) are compared exactly; floats within rel 1e-5 (north_star tolerance)."""
+import dataclasses
+
 import numpy as np
 import pytest
 import torch
@@ -23,8 +25,12 @@ CASES = [
 ]
 
 
-def _run(spec_name, gids, sf, params=None):
-    spec, batch = make_batch(spec_name, gids, scale_factor=sf)
+def _run(spec_name, gids, sf, params=None, spec=None):
+    if spec is None:
+        spec, batch = make_batch(spec_name, gids, scale_factor=sf)
+    else:
+        from aod_meh_hua_b200.synth import SyntheticPool
+        batch = SyntheticPool(spec, seed0=20, device="cpu", scale_factor=sf).batch(list(gids))
     params = params or ScoringParams()
     out, rec = run_oracle(spec, batch, params)
     sc = Scorer(spec, params, max_batch=len(gids), device="cuda:0")
@@ -48,9 +54,41 @@ def _run(spec_name, gids, sf, params=None):
     return spec, batch, out, rec, res, st
 
 
+def _random_specs():
+    """Seeded random detector geometries: odd image sizes (ragged last tiles, 1-row levels), class
+    counts with and without a template instantiation, small nms_pre so that sparse-gather, dense-rescan
+    and keep-everything levels all occur, shifted thresholds."""
+    from aod_meh_hua_b200.specs import retina_spec, ssd_spec
+    rs = np.random.RandomState(77)
+    out = []
+    for i in range(8):
+        h, w = int(rs.randint(40, 200)), int(rs.randint(40, 230))
+        c = int(rs.choice([2, 3, 5, 20, 33, 80]))
+        spec = retina_spec(f"rand_retina_{i}", h, w, c, nms_pre=int(rs.choice([17, 64, 200, 1000])),
+                           gt_range=(1, 4))
+        spec = dataclasses.replace(spec, score_thr=float(rs.choice([0.02, 0.05, 0.2])),
+                                   max_per_img=int(rs.choice([5, 30, 100])), nms_iou=float(rs.choice([0.3, 0.5, 0.7])))
+        out.append((spec, [i, i + 1, i + 2][: int(rs.randint(1, 4))],
+                    (1.0, 1.0, 1.0, 1.0) if i % 2 else (1.31, 0.77, 1.31, 0.77)))
+    for i in range(3):
+        spec = ssd_spec(f"rand_ssd_{i}", 300, int(rs.choice([1, 4, 20])), nms_pre=int(rs.choice([30, 150, 1000])),
+                        gt_range=(1, 4))
+        spec = dataclasses.replace(spec, max_per_img=int(rs.choice([10, 200])))
+        out.append((spec, [i, i + 5], (1.0, 1.0, 1.0, 1.0)))
+    return out
+
+
+@pytest.mark.parametrize("spec,gids,sf", _random_specs(), ids=lambda v: getattr(v, "name", None))
+def test_stagewise_parity_random_geometry(spec, gids, sf):
+    _check_stagewise(*_run(None, gids, sf, spec=spec), gids)
+
+
 @pytest.mark.parametrize("spec_name,gids,sf", CASES)
 def test_stagewise_parity(spec_name, gids, sf):
-    spec, batch, out, rec, res, st = _run(spec_name, gids, sf)
+    _check_stagewise(*_run(spec_name, gids, sf), gids)
+
+
+def _check_stagewise(spec, batch, out, rec, res, st, gids):
     B, S, C = len(gids), spec.num_levels, spec.c_out
     koff = np.concatenate([[0], np.cumsum(spec.level_k)])
 
