@@ -78,7 +78,7 @@ __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_wa
 // both tests are done as log2(U2) <= rhs.
 __device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const float f0, const float f1,
                                            const unsigned s_small, const unsigned s_cst4, unsigned& c, float& l2) {
-  // f0, f1 in [1,2): U1 = f0 - 1 (22-bit resolution), U2 = f1 - 1 + 2^-21 in (0,1) (20-bit)
+  // f0, f1 in [1,2): U1 = f0 - 1 = (k + 1/2) / 2^16, U2 = f1 - 1 + 2^-17 in (0,1) (16-bit each)
   const unsigned ii = (unsigned)min(i, nsmall - 1);
   c = lds_u8(s_small + ii);
   const float4 k = lds_v4(s_cst4 + ii * 16u);           // b, 1/alpha, alpha-1, -b (list order)
@@ -92,18 +92,15 @@ __device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const 
   const float rhsb = k.z * l2b;                         // log2 x^(alpha-1)
   l2 = lo ? l2a : l2b;
   const float rhs = lo ? rhsa : rhsb;
-  return (i < nsmall) & (lg2_approx(f1 - 0.99999952316284180f) <= rhs);   // f1 - (1 - 2^-21)
+  return (i < nsmall) & (lg2_approx(f1 - 0.99999237060546875f) <= rhs);   // f1 - (1 - 2^-17)
 }
 
-// One Philox4x32 block (128 bits) -> three (U1, U2) pairs: 22 + 20 bits each, as floats in [1,2)
-// built straight from the bits (no int->float conversion on the SFU pipe).
-__device__ __forceinline__ void split_block(const uint4 w, float (&f0)[3], float (&f1)[3]) {
-  f0[0] = __uint_as_float(0x3f800000u | ((w.x >> 9) & 0x7ffffeu));                         // w.x[31:10]
-  f1[0] = __uint_as_float(0x3f800000u | ((__funnelshift_r(w.y, w.x, 22) & 0xfffffu) << 3)); // w.x[9:0] : w.y[31:22]
-  f0[1] = __uint_as_float(0x3f800000u | ((w.y << 1) & 0x7ffffeu));                         // w.y[21:0]
-  f1[1] = __uint_as_float(0x3f800000u | ((w.z >> 9) & 0x7ffff8u));                         // w.z[31:12]
-  f0[2] = __uint_as_float(0x3f800000u | ((__funnelshift_r(w.w, w.z, 22) & 0x3fffffu) << 1)); // w.z[11:0] : w.w[31:22]
-  f1[2] = __uint_as_float(0x3f800000u | ((w.w << 1) & 0x7ffff8u));                         // w.w[21:2]
+// One Philox4x32 word -> one (U1, U2) pair, 16 bits each, as floats in [1,2) built straight from
+// the bits (no int->float conversion on the SFU pipe): the 16 bits go to the top of the mantissa,
+// U1 gets a half-step offset so that b*U1 is never 0.
+__device__ __forceinline__ void split_word(const unsigned w, float& f0, float& f1) {
+  f0 = __uint_as_float(0x3f800040u | ((w >> 9) & 0x7fff80u));     // w[31:16]
+  f1 = __uint_as_float(0x3f800000u | ((w << 7) & 0x7fff80u));     // w[15:0]
 }
 
 __global__ void __launch_bounds__(kK2Threads, 3)
@@ -256,25 +253,32 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
           unsigned addr = a_lrow;
           for (int c = 0; c < C; ++c, addr += kLStride * 2u) sts_bf16(addr, 0.f);
         }
-        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with three cursors (list positions
-        // mod 3): each iteration one Philox block (128 bits = 3 x (22 + 20)) feeds one attempt per
+        // Ahrens-Dieter GS for alpha < 1.  Flattened rejection loop with four cursors (list positions
+        // mod 4): each iteration one Philox block (4 words = 4 x (16 + 16) bits) feeds one attempt per
         // cursor, so a lane never idles while a neighbour retries and the attempts overlap in the pipes.
-        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall, ic = active ? 2 : nsmall;
+        int ia = active ? 0 : nsmall, ib = active ? 1 : nsmall, ic = active ? 2 : nsmall, id = active ? 3 : nsmall;
         unsigned kcall = 0;
         if (nsmall > 0) {
-          while (__any_sync(full, (ia < nsmall) | (ib < nsmall) | (ic < nsmall))) {
-            float f0[3], f1[3];
-            split_block(philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key), f0, f1);
-            unsigned ca, cb, cc;
-            float la, lb, lc;
+          while (__any_sync(full, (ia < nsmall) | (ib < nsmall) | (ic < nsmall) | (id < nsmall))) {
+            const uint4 w = philox4x32_10(make_uint4((unsigned)t, kcall++, pid, gid), key);
+            float f0[4], f1[4];
+            split_word(w.x, f0[0], f1[0]);
+            split_word(w.y, f0[1], f1[1]);
+            split_word(w.z, f0[2], f1[2]);
+            split_word(w.w, f0[3], f1[3]);
+            unsigned ca, cb, cc, cd;
+            float la, lb, lc, ld;
             const bool oka = gs_attempt(ia, nsmall, f0[0], f1[0], a_small, a_cst4, ca, la);
             const bool okb = gs_attempt(ib, nsmall, f0[1], f1[1], a_small, a_cst4, cb, lb);
             const bool okc = gs_attempt(ic, nsmall, f0[2], f1[2], a_small, a_cst4, cc, lc);
-            const float da = fmaxf(la - m, -300.f), db = fmaxf(lb - m, -300.f), dc = fmaxf(lc - m, -300.f);
-            const float ea = ex2_approx(da), eb = ex2_approx(db), ec = ex2_approx(dc);
-            if (oka) { sts_bf16(a_lrow + ca * (kLStride * 2u), ea); asum += ea; bs = fmaf(ea, da, bs); ia += 3; }
-            if (okb) { sts_bf16(a_lrow + cb * (kLStride * 2u), eb); asum += eb; bs = fmaf(eb, db, bs); ib += 3; }
-            if (okc) { sts_bf16(a_lrow + cc * (kLStride * 2u), ec); asum += ec; bs = fmaf(ec, dc, bs); ic += 3; }
+            const bool okd = gs_attempt(id, nsmall, f0[3], f1[3], a_small, a_cst4, cd, ld);
+            const float da = fmaxf(la - m, -300.f), db = fmaxf(lb - m, -300.f);
+            const float dc = fmaxf(lc - m, -300.f), dd = fmaxf(ld - m, -300.f);
+            const float ea = ex2_approx(da), eb = ex2_approx(db), ec = ex2_approx(dc), ed = ex2_approx(dd);
+            if (oka) { sts_bf16(a_lrow + ca * (kLStride * 2u), ea); asum += ea; bs = fmaf(ea, da, bs); ia += 4; }
+            if (okb) { sts_bf16(a_lrow + cb * (kLStride * 2u), eb); asum += eb; bs = fmaf(eb, db, bs); ib += 4; }
+            if (okc) { sts_bf16(a_lrow + cc * (kLStride * 2u), ec); asum += ec; bs = fmaf(ec, dc, bs); ic += 4; }
+            if (okd) { sts_bf16(a_lrow + cd * (kLStride * 2u), ed); asum += ed; bs = fmaf(ed, dd, bs); id += 4; }
           }
         }
         float inv_a = 0.f;
