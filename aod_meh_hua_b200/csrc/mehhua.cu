@@ -1,6 +1,7 @@
 // C ABI of the mehhua scoring path (see include/mehhua.h).  Host side: argument validation, the
 // batch Plan, workspace carving and kernel launches.  No torch types, no hidden allocation except
 // inside the explicit host-buffer context.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -124,12 +125,14 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
 size_t carve(const Plan& p, void* base, Workspace* ws) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  // the status word and the work counter come first: their addresses do not depend on the batch size,
+  // so a workspace used with different B (host-buffer chunks, partial last batches) keeps one status
+  const size_t o_status = take(sizeof(unsigned));
+  const size_t o_work = take(4 * sizeof(int));
   const size_t o_keys = take((size_t)p.B * p.N * sizeof(float));
   const size_t o_cand = take((size_t)p.B * p.K * p.num_fg * sizeof(unsigned long long));
   const size_t o_cnt = take((size_t)p.B * sizeof(int));
   const size_t o_maxc = take((size_t)p.B * sizeof(unsigned));
-  const size_t o_status = take(sizeof(unsigned));
-  const size_t o_work = take(4 * sizeof(int));
   const size_t o_inv = take((size_t)p.B * p.N * sizeof(int));
   const size_t o_fgl = take((size_t)p.B * p.pair_cap * sizeof(unsigned));
   const size_t o_fgc = take((size_t)p.B * sizeof(int));
@@ -570,13 +573,17 @@ int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 // ---------------------------------------------------------------------------------------------
 // host-buffer context
 // ---------------------------------------------------------------------------------------------
+constexpr int kHostChunks = 4;      // a host batch is uploaded in up to 4 image chunks; chunk j is scored
+                                    // while chunk j+1 is still on the PCIe link
 struct mehhua_host_ctx {
   mehhua_config_t cfg;
   mehhua_level_t shapes[MEHHUA_MAX_LEVELS];
   mehhua_level_t dev[MEHHUA_MAX_LEVELS];
   int max_batch;
   int64_t K;
-  cudaStream_t stream;
+  cudaStream_t stream;       // compute (and result read-back)
+  cudaStream_t copy_stream;  // host -> device input chunks, overlapped with the compute of earlier chunks
+  cudaEvent_t chunk_ready[kHostChunks];
   void* arena;          // one device allocation holding inputs, outputs, workspace
   size_t arena_bytes;
   void* workspace;
@@ -656,7 +663,11 @@ int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* lev
   carve(p, c->workspace, &ws);
   c->status = ws.status;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  for (int j = 0; j < kHostChunks && e == cudaSuccess; ++j)
+    e = cudaEventCreateWithFlags(&c->chunk_ready[j], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->workspace, 0, c->workspace_bytes, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) { cudaFree(c->arena); delete c; return cuda_fail(e, "host ctx stream setup"); }
   *ctx_out = c;
   return 0;
@@ -664,7 +675,10 @@ int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* lev
 
 void mehhua_host_ctx_destroy(mehhua_host_ctx_t* c) {
   if (!c) return;
+  cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->stream);
+  for (int j = 0; j < kHostChunks; ++j) cudaEventDestroy(c->chunk_ready[j]);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   cudaFree(c->arena);
   delete c;
@@ -675,33 +689,62 @@ int mehhua_score_batch_host(mehhua_host_ctx_t* c, const mehhua_level_t* lh, int3
                             float* image_scores_host, uint32_t* status_out) {
   if (!c || !lh || !img_shapes_host || !scale_factors_host || !image_scores_host) return arg_fail("null host pointer");
   if (B < 1 || B > c->max_batch) return arg_fail("batch exceeds the context's max_batch");
-  cudaStream_t st = c->stream;
+  cudaStream_t st = c->stream, cp = c->copy_stream;
   const int S = c->cfg.num_levels, C = c->cfg.c_out;
   for (int s = 0; s < S; ++s) {
     if (lh[s].H != c->shapes[s].H || lh[s].W != c->shapes[s].W || lh[s].A != c->shapes[s].A)
       return arg_fail("level geometry differs from the context's");
-    const size_t n = (size_t)lh[s].H * lh[s].W * lh[s].A;
     if (!lh[s].logits || !lh[s].deltas || !lh[s].lambda) return arg_fail("null host level pointer");
-    CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].logits), lh[s].logits, (size_t)B * n * C * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].deltas), lh[s].deltas, (size_t)B * n * 16, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].lambda), lh[s].lambda, (size_t)B * n * 4, cudaMemcpyHostToDevice, st));
-    if (lh[s].anchors) {
-      CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].anchors), lh[s].anchors, n * 16, cudaMemcpyHostToDevice, st));
-    } else if (!c->anchors_loaded) {
-      return arg_fail("anchors must be given on the first call");
-    }
+    if (!lh[s].anchors && !c->anchors_loaded) return arg_fail("anchors must be given on the first call");
+  }
+  // per-batch small inputs and (when given) the anchors go first on the copy stream
+  for (int s = 0; s < S; ++s) {
+    const size_t n = (size_t)lh[s].H * lh[s].W * lh[s].A;
+    if (lh[s].anchors)
+      CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].anchors), lh[s].anchors, n * 16, cudaMemcpyHostToDevice, cp));
   }
   c->anchors_loaded = true;
-  CU(cudaMemcpyAsync(c->img_shapes, img_shapes_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c->scale_factors, scale_factors_host, (size_t)B * 16, cudaMemcpyHostToDevice, st));
-  const int64_t* ids = nullptr;
-  if (image_ids_host) {
-    CU(cudaMemcpyAsync(c->image_ids, image_ids_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    ids = c->image_ids;
+  CU(cudaMemcpyAsync(c->img_shapes, img_shapes_host, (size_t)B * 8, cudaMemcpyHostToDevice, cp));
+  CU(cudaMemcpyAsync(c->scale_factors, scale_factors_host, (size_t)B * 16, cudaMemcpyHostToDevice, cp));
+  std::vector<int64_t> iota;
+  if (!image_ids_host) {      // default Philox image id = position in the batch (not in the chunk)
+    iota.resize(B);
+    for (int b = 0; b < B; ++b) iota[b] = b;
+    image_ids_host = iota.data();
   }
-  int rc = mehhua_score_batch(&c->cfg, c->dev, B, c->img_shapes, c->scale_factors, ids, &c->bufs, c->workspace,
-                              c->workspace_bytes, st);
-  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->image_ids, image_ids_host, (size_t)B * 8, cudaMemcpyHostToDevice, cp));
+  // image chunks: upload chunk j on the copy stream, score it on the compute stream as soon as it has
+  // landed - the path of chunk j overlaps the upload of chunk j+1, only the last chunk's is exposed
+  const int nchunks = B >= 2 * kHostChunks ? kHostChunks : 1;
+  const int cb = (B + nchunks - 1) / nchunks;
+  int used = 0;
+  for (int j0 = 0; j0 < B; j0 += cb, ++used) {
+    const int nb = std::min(cb, B - j0);
+    for (int s = 0; s < S; ++s) {
+      const size_t n = (size_t)lh[s].H * lh[s].W * lh[s].A;
+      CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].logits) + (size_t)j0 * n * C, lh[s].logits + (size_t)j0 * n * C,
+                         (size_t)nb * n * C * 4, cudaMemcpyHostToDevice, cp));
+      CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].deltas) + (size_t)j0 * n * 4, lh[s].deltas + (size_t)j0 * n * 4,
+                         (size_t)nb * n * 16, cudaMemcpyHostToDevice, cp));
+      CU(cudaMemcpyAsync(const_cast<float*>(c->dev[s].lambda) + (size_t)j0 * n, lh[s].lambda + (size_t)j0 * n,
+                         (size_t)nb * n * 4, cudaMemcpyHostToDevice, cp));
+    }
+    CU(cudaEventRecord(c->chunk_ready[used], cp));
+    CU(cudaStreamWaitEvent(st, c->chunk_ready[used], 0));
+    mehhua_level_t lv[MEHHUA_MAX_LEVELS];
+    for (int s = 0; s < S; ++s) {
+      const size_t n = (size_t)lh[s].H * lh[s].W * lh[s].A;
+      lv[s] = c->dev[s];
+      lv[s].logits = c->dev[s].logits + (size_t)j0 * n * C;
+      lv[s].deltas = c->dev[s].deltas + (size_t)j0 * n * 4;
+      lv[s].lambda = c->dev[s].lambda + (size_t)j0 * n;
+    }
+    mehhua_buffers_t bufs = c->bufs;            // chunks run back to back on one stream: they share the
+    bufs.image_scores = c->bufs.image_scores + j0;   // intermediate buffers, only the scores are kept apart
+    const int rc = mehhua_score_batch(&c->cfg, lv, nb, c->img_shapes + 2 * j0, c->scale_factors + 4 * j0,
+                                      c->image_ids + j0, &bufs, c->workspace, c->workspace_bytes, st);
+    if (rc) { cudaStreamSynchronize(cp); cudaStreamSynchronize(st); return rc; }
+  }
   CU(cudaMemcpyAsync(image_scores_host, c->bufs.image_scores, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   unsigned status = 0;
   CU(cudaMemcpyAsync(&status, c->status, 4, cudaMemcpyDeviceToHost, st));

@@ -375,3 +375,44 @@ def test_scoring_stage_writes_the_cycle_files(tmp_path):
     cfg = _Cfg(uncertainty_pool="Random", uncertainty_type="Epistemic", uncertainty_pool2="x", X_S_size=2, work_dir=str(tmp_path))
     perm = calculate_uncertainty(cfg, Model(), loader, scaleUnc=False)
     assert sorted(perm.tolist()) == list(range(6))
+
+
+@pytest.mark.parametrize("B,max_batch,explicit_ids", [(9, 9, True), (10, 12, True), (11, 16, False)])
+def test_host_buffer_chunked_upload_matches_device_path(B, max_batch, explicit_ids):
+    """mehhua_score_batch_host uploads a batch in up to four image chunks and scores chunk j while
+    chunk j+1 is on the link: scores (and the default Philox ids = position in the BATCH) must not
+    depend on the chunking, also when B < max_batch and the last chunk is ragged."""
+    import ctypes as C
+    from aod_meh_hua_b200.scoring import Scorer
+    gids = list(range(B))
+    spec, batch = make_batch("tiny_retina_coco", gids)
+    params = ScoringParams(n_samples=32)
+    sc = Scorer(spec, params, max_batch=B, device="cuda:0")
+    res = sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                   batch["scale_factors"], image_ids=gids)       # ids 0..B-1 = the host entry's default
+    want = res.image_scores.cpu().numpy().copy()
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    _lib.check(lib.mehhua_host_ctx_create(C.byref(sc.cfg), sc._shape_levels, max_batch, C.byref(ctx)), "ctx")
+    lv = _lib.LevelArray()
+    keep = []
+    for s in range(spec.num_levels):
+        a, b_, c, d = (batch["cls_scores"][s].contiguous().pin_memory(), batch["bbox_preds"][s].contiguous().pin_memory(),
+                       batch["L_scores"][s].contiguous().pin_memory(), batch["anchors"][s].contiguous())
+        keep += [a, b_, c, d]
+        lv[s].logits, lv[s].deltas, lv[s].lam, lv[s].anchors = a.data_ptr(), b_.data_ptr(), c.data_ptr(), d.data_ptr()
+        (lv[s].H, lv[s].W), lv[s].A = spec.featmaps[s], spec.num_anchors[s]
+    shp = np.asarray([[spec.img_hw[0], spec.img_hw[1]]] * B, dtype=np.float32)
+    sf = np.ones((B, 4), dtype=np.float32)
+    ids = np.arange(B, dtype=np.int64)
+    st = C.c_uint32(0)
+    for rep in range(2):                                 # second call: anchors already resident
+        out = np.zeros(B, dtype=np.float32)
+        if rep == 1:
+            for s in range(spec.num_levels):
+                lv[s].anchors = None
+        _lib.check(lib.mehhua_score_batch_host(ctx, lv, B, shp.ctypes.data, sf.ctypes.data,
+                                               ids.ctypes.data if explicit_ids else None, out.ctypes.data, C.byref(st)), "host")
+        assert np.array_equal(out, want), (rep, out, want)
+        assert st.value & (_lib.ST_PAIR_OVERFLOW | _lib.ST_BAD_ALPHA) == 0
+    lib.mehhua_host_ctx_destroy(ctx)
