@@ -55,6 +55,8 @@ struct Workspace {
   unsigned* cand_maxc;         // [B]      max candidate box coordinate, ordered-uint encoded
   unsigned* status;            // [1]
   int* work_counter;           // [4]      dynamic work queues
+  int* k2_done;                // [kK2SplitPairs] arrival counters of split K2 pairs
+  float* k2_part;              // [kK2SplitPairs, kK2Sub, C+1] partial class / entropy sums of split K2 pairs
   int* inv_map;                // [B, N]   position -> row of the dense top-k levels (-1 = not kept)
   unsigned* fg_list;           // [B, pair_cap] Entropy_ALL: (level << 28 | prior) of every foreground prior
   int* fg_cnt;                 // [B]

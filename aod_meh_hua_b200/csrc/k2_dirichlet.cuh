@@ -32,7 +32,14 @@ constexpr int kK2Warps = kK2Threads / 32;
 constexpr int kLStride = 34;                          // bf16 elements per class row (17 words)
 constexpr float kFltMin = 1.17549435e-38f;
 constexpr float kInvE = 0.36787944117144233f;
-constexpr float kTwoM32 = 2.3283064365386963e-10f;   // 2^-32
+// The T samples of a pair are accumulated in kK2Sub fixed sub-ranges (whole 32-sample rounds) whose
+// partial sums are combined in sub-range order.  The arithmetic is the same whether one warp walks
+// all sub-ranges or - when a launch has too few pairs to fill the GPU (the reference's own batch
+// sizes of 2 and 8 images) - kK2Sub warps take one each and the last to finish combines them, so a
+// score does not depend on the batch it was computed in.
+constexpr int kK2Sub = 4;
+constexpr int kK2SplitPairs = 8192;                  // launches with at most this many pairs are split
+__host__ __device__ inline size_t k2_part_floats(int C) { return (size_t)kK2SplitPairs * kK2Sub * ((size_t)C + 1); }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -63,9 +70,9 @@ __device__ __forceinline__ void sts_bf16(unsigned a, float v) {      // round-to
 __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // per-warp shared memory, in floats:
-//   cst4[C] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*17 words] | alpha[C] | avg[C] | lists 3 x C bytes
+//   cst4[C] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*17 words] | alpha[C] | avg[C] | part[C] | lists 3 x C bytes
 __host__ __device__ inline size_t k2_warp_floats(int C) {
-  const size_t f = 4 * (size_t)C + (size_t)C * (kLStride / 2) + 2 * (size_t)C + (3 * (size_t)C + 3) / 4;
+  const size_t f = 4 * (size_t)C + (size_t)C * (kLStride / 2) + 3 * (size_t)C + (3 * (size_t)C + 3) / 4;
   return (f + 3) & ~(size_t)3;
 }
 __host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_warp_floats(C) * sizeof(float) + 1040 * sizeof(int); }
@@ -103,6 +110,10 @@ __device__ __forceinline__ void split_word(const unsigned w, float& f0, float& f
   f1 = __uint_as_float(0x3f800000u | ((w << 7) & 0x7fff80u));     // w[15:0]
 }
 
+// SPLIT = false: one work item per pair (many pairs, or injected samples); SPLIT = true: one item per
+// (pair, sub-range).  Both instantiations are launched; the one whose regime does not apply returns
+// at once (the pair count is only known on the device).
+template <bool SPLIT>
 __global__ void __launch_bounds__(kK2Threads, 3)
 k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ score_rows,
                     const float* __restrict__ lam_rows, const float* __restrict__ lam_mean,
@@ -110,7 +121,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
                     const int* __restrict__ pair_off, const long long* __restrict__ image_ids,
                     const float* __restrict__ inj, const long long* __restrict__ inj_off,
                     float* __restrict__ pair_unc, int* __restrict__ work_counter,
-                    unsigned* __restrict__ status) {
+                    float* __restrict__ part, int* __restrict__ done, unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k2_smem[];
   const int C = p.C, T = p.n_samples;
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
@@ -119,7 +130,8 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   unsigned* lbuf = reinterpret_cast<unsigned*>(wbase + 4 * C);   // [C][17 words] = [C][34] bf16
   float* s_alpha = wbase + 4 * C + C * (kLStride / 2);        // [C]
   float* s_avg = s_alpha + C;                                 // [C]
-  unsigned char* s_small = reinterpret_cast<unsigned char*>(s_avg + C);
+  float* s_part = s_avg + C;                                  // [C] class sums of the current sub-range
+  unsigned char* s_small = reinterpret_cast<unsigned char*>(s_part + C);
   unsigned char* s_big = s_small + C;
   unsigned char* s_bad = s_big + C;
   const int lane = threadIdx.x & 31;
@@ -138,12 +150,23 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   const unsigned lt_mask = (1u << lane) - 1u;
   const uint2 key = make_uint2((unsigned)(p.seed & 0xffffffffull), (unsigned)(p.seed >> 32));
   const float fT = (float)T;
+  // sub-ranges of the sample index: whole rounds of 32, kK2Sub of them
+  const int sub_len = (((T + 31) / 32 + kK2Sub - 1) / kK2Sub) * 32;
+  // few pairs and no injected samples: one work item per (pair, sub-range) instead of per pair
+  const bool split_regime = (inj == nullptr && total <= kK2SplitPairs);
+  if (split_regime != SPLIT) return;
+  constexpr int nsplit = SPLIT ? kK2Sub : 1;
+  const int items = total * nsplit;
 
   for (;;) {
     int g = 0;
     if (lane == 0) g = atomicAdd(work_counter, 1);
     g = __shfl_sync(full, g, 0);
-    if (g >= total) break;
+    if (g >= items) break;
+    const int gp = SPLIT ? g % total : g;                    // pair (index over the whole launch)
+    const int sub0 = SPLIT ? g / total : 0;                  // first sub-range of this item
+    const int sub1 = SPLIT ? sub0 + 1 : kK2Sub;
+    g = gp;
     // locate (image, pair) by binary search in the prefix
     int lo = 0, hi = p.B;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (img_pref[mid] <= g) lo = mid; else hi = mid; }
@@ -213,7 +236,12 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       // ---- free-running sampler (log2 units throughout) ----
       const unsigned gid = image_ids ? (unsigned)image_ids[b] : (unsigned)b;
       const unsigned pid = (unsigned)row | ((unsigned)obj << 20);
-      for (int t0 = 0; t0 < T; t0 += 32) {
+      for (int sub = sub0; sub < sub1; ++sub) {
+      for (int c = lane; c < C; c += 32) s_part[c] = 0.f;
+      float ent_sub = 0.f;
+      __syncwarp();
+      const int t_end = min(T, (sub + 1) * sub_len);
+      for (int t0 = sub * sub_len; t0 < t_end; t0 += 32) {
         const int t = t0 + lane;
         const bool active = t < T;
         // Normalisation is a log-sum-exp around a reference exponent m fixed BEFORE the draws:
@@ -284,7 +312,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         float inv_a = 0.f;
         if (active && asum > 0.f) {
           inv_a = __fdividef(1.f, asum);
-          ent_acc += logf(asum) - kLn2 * bs * inv_a;
+          ent_sub += logf(asum) - kLn2 * bs * inv_a;
         }
         __syncwarp();
         // class sums over the 32 samples, transposed: lane = class, walk the samples two at a time
@@ -307,12 +335,44 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
             if (rem > 64) { u = r2p[w]; a2 = fmaf(__uint_as_float(u << 16), iv0, a2); a2 = fmaf(__uint_as_float(u & 0xffff0000u), iv1, a2); }
             if (rem > 96) { u = r3p[w]; a3 = fmaf(__uint_as_float(u << 16), iv0, a3); a3 = fmaf(__uint_as_float(u & 0xffff0000u), iv1, a3); }
           }
-          if (c < C) s_avg[c] += a0;
-          if (c + 32 < C) s_avg[c + 32] += a1;
-          if (c + 64 < C) s_avg[c + 64] += a2;
-          if (c + 96 < C) s_avg[c + 96] += a3;
+          if (c < C) s_part[c] += a0;
+          if (c + 32 < C) s_part[c + 32] += a1;
+          if (c + 64 < C) s_part[c + 64] += a2;
+          if (c + 96 < C) s_part[c + 96] += a3;
         }
         __syncwarp();
+      }
+      // close the sub-range: its class sums and entropy sum, combined in sub-range order
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ent_sub += __shfl_xor_sync(full, ent_sub, o);
+      if constexpr (!SPLIT) {
+        for (int c = lane; c < C; c += 32) s_avg[c] += s_part[c];
+        ent_acc += ent_sub;
+      } else {
+        float* dst = part + ((size_t)gp * kK2Sub + sub) * (C + 1);
+        for (int c = lane; c < C; c += 32) __stcg(dst + c, s_part[c]);
+        if (lane == 0) __stcg(dst + C, ent_sub);
+      }
+      __syncwarp();
+      }
+      if constexpr (SPLIT) {
+        // the last of the pair's kK2Sub items to arrive combines the partial sums (in sub-range order)
+        __threadfence();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(done + gp, 1);
+        old = __shfl_sync(full, old, 0);
+        if (old != nsplit - 1) continue;
+        __threadfence();
+        const float* src = part + (size_t)gp * kK2Sub * (C + 1);
+        for (int c = lane; c < C; c += 32) {
+          float v = 0.f;
+#pragma unroll
+          for (int u = 0; u < kK2Sub; ++u) v += __ldcg(src + (size_t)u * (C + 1) + c);
+          s_avg[c] = v;
+        }
+        ent_acc = 0.f;
+#pragma unroll
+        for (int u = 0; u < kK2Sub; ++u) ent_acc += __ldcg(src + (size_t)u * (C + 1) + C);
       }
     }
     __syncwarp();
@@ -325,7 +385,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       tot += __shfl_xor_sync(full, tot, o);
-      ent_acc += __shfl_xor_sync(full, ent_acc, o);
+      if (ioff >= 0) ent_acc += __shfl_xor_sync(full, ent_acc, o);   // injection: per-lane sums; else already reduced
     }
     if (lane == 0) {
       const float ale = __fdiv_rn(ent_acc, fT);

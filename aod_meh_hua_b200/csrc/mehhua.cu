@@ -129,6 +129,8 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   // so a workspace used with different B (host-buffer chunks, partial last batches) keeps one status
   const size_t o_status = take(sizeof(unsigned));
   const size_t o_work = take(4 * sizeof(int));
+  const size_t o_k2done = take((size_t)kK2SplitPairs * sizeof(int));
+  const size_t o_k2part = take(k2_part_floats(p.C) * sizeof(float));
   const size_t o_keys = take((size_t)p.B * p.N * sizeof(float));
   const size_t o_cand = take((size_t)p.B * p.K * p.num_fg * sizeof(unsigned long long));
   const size_t o_cnt = take((size_t)p.B * sizeof(int));
@@ -145,6 +147,8 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
     ws->cand_maxc = reinterpret_cast<unsigned*>(b + o_maxc);
     ws->status = reinterpret_cast<unsigned*>(b + o_status);
     ws->work_counter = reinterpret_cast<int*>(b + o_work);
+    ws->k2_done = reinterpret_cast<int*>(b + o_k2done);
+    ws->k2_part = reinterpret_cast<float*>(b + o_k2part);
     ws->inv_map = reinterpret_cast<int*>(b + o_inv);
     ws->fg_list = reinterpret_cast<unsigned*>(b + o_fgl);
     ws->fg_cnt = reinterpret_cast<int*>(b + o_fgc);
@@ -342,7 +346,8 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
   if (p.C > 256) return arg_fail("c_out must be <= 256 for the K2 class lists");
   const size_t smem = k2_smem_bytes(p.C);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K2 shared-memory layout");
-  if (int rc = ensure_dyn_smem(k2_dirichlet_kernel, smem)) return rc;
+  if (int rc = ensure_dyn_smem(k2_dirichlet_kernel<false>, smem)) return rc;
+  if (int rc = ensure_dyn_smem(k2_dirichlet_kernel<true>, smem)) return rc;
   int blocks_per_sm = 1;
   {   // resident blocks per SM for this (device, shared-memory size): the persistent grid's width
     static std::mutex mu;
@@ -352,17 +357,31 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
     std::lock_guard<std::mutex> lock(mu);
     int& v = cache[{dev, smem}];
     if (v == 0) {
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k2_dirichlet_kernel, kK2Threads, smem));
-      if (v < 1) v = 1;
+      int v0 = 0, v1 = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v0, k2_dirichlet_kernel<false>, kK2Threads, smem));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v1, k2_dirichlet_kernel<true>, kK2Threads, smem));
+      v = std::max(1, std::min(v0, v1));
     }
     blocks_per_sm = v;
   }
-  CU(cudaMemsetAsync(ws.work_counter, 0, sizeof(int), st));
-  k2_dirichlet_kernel<<<sm_count() * blocks_per_sm, kK2Threads, smem, st>>>(
-      p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off,
-      reinterpret_cast<const long long*>(image_ids), inj, reinterpret_cast<const long long*>(inj_off),
-      o->pair_unc, ws.work_counter, ws.status);
+  // work_counter[0] / [1]: the queues of the per-pair and the per-(pair, sub-range) instantiation
+  CU(cudaMemsetAsync(ws.work_counter, 0, 2 * sizeof(int), st));
+  const long long* ids = reinterpret_cast<const long long*>(image_ids);
+  const long long* ioff = reinterpret_cast<const long long*>(inj_off);
+  const int grid = sm_count() * blocks_per_sm;
+  // the pair count lives on the device: both regimes are launched, the one that does not apply returns
+  // at once.  Injected samples (tests) always take the per-pair form.
+  k2_dirichlet_kernel<false><<<grid, kK2Threads, smem, st>>>(
+      p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off, ids, inj, ioff,
+      o->pair_unc, ws.work_counter, ws.k2_part, ws.k2_done, ws.status);
   LAUNCHED("k2_dirichlet_kernel");
+  if (inj == nullptr) {
+    CU(cudaMemsetAsync(ws.k2_done, 0, (size_t)kK2SplitPairs * sizeof(int), st));
+    k2_dirichlet_kernel<true><<<grid, kK2Threads, smem, st>>>(
+        p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off, ids, inj, ioff,
+        o->pair_unc, ws.work_counter + 1, ws.k2_part, ws.k2_done, ws.status);
+    LAUNCHED("k2_dirichlet_kernel(split)");
+  }
   return 0;
 }
 

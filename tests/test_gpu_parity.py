@@ -422,3 +422,28 @@ def test_pool_topk_randomised_against_numpy():
             order = np.argsort(x[cand], kind="stable")
             want = cand[order[-k:]][::-1] if k <= len(cand) else cand[order][::-1]
             assert np.array_equal(got, want), (n, k, x[:5])
+
+
+def test_scores_do_not_depend_on_the_batch_they_were_computed_in():
+    """K2 splits the samples of a pair over four warps when a launch has few pairs (<= 8192) and lets
+    one warp walk them otherwise; both orders of work combine the same four partial sums in the same
+    order, so an image's score is bit-identical whether it is scored in a batch of 2 or of 24."""
+    spec, batch = make_batch("cfg1_retina_r50_512_voc", list(range(24)))
+    params = ScoringParams(n_samples=100)
+    big = Scorer(spec, params, max_batch=24, device="cuda:0")
+    res = big.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                    batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    assert int(res.pair_off[:, -1].sum()) > 8192, "the large batch must take the unsplit path"
+    want = res.image_scores.cpu().numpy().copy()
+    unc_big = [res.pair_unc[b, : int(res.pair_off[b, -1])].cpu().numpy().copy() for b in range(24)]
+    small = Scorer(spec, params, max_batch=2, device="cuda:0")
+    for lo in range(0, 24, 2):
+        sl = slice(lo, lo + 2)
+        r = small.score([t[sl] for t in batch["cls_scores"]], [t[sl] for t in batch["bbox_preds"]],
+                        [t[sl] for t in batch["L_scores"]], batch["anchors"], batch["img_shapes"][sl],
+                        batch["scale_factors"][sl], image_ids=batch["gids"][sl])
+        assert int(r.pair_off[:, -1].sum()) <= 8192
+        for j in range(2):
+            n = int(r.pair_off[j, -1])
+            assert np.array_equal(r.pair_unc[j, :n].cpu().numpy(), unc_big[lo + j])
+        assert np.array_equal(r.image_scores.cpu().numpy(), want[sl])
