@@ -75,7 +75,11 @@ __host__ __device__ inline size_t k2_warp_floats(int C) {
   const size_t f = 4 * (size_t)C + (size_t)C * (kLStride / 2) + 3 * (size_t)C + (3 * (size_t)C + 3) / 4;
   return (f + 3) & ~(size_t)3;
 }
-__host__ __device__ inline size_t k2_smem_bytes(int C) { return kK2Warps * k2_warp_floats(C) * sizeof(float) + 1040 * sizeof(int); }
+// + the per-image pair-count prefix [B+1], padded to 16 ints
+__host__ __device__ inline int k2_pref_ints(int B) { return (B + 1 + 15) & ~15; }
+__host__ __device__ inline size_t k2_smem_bytes(int C, int B) {
+  return kK2Warps * k2_warp_floats(C) * sizeof(float) + k2_pref_ints(B) * sizeof(int);
+}
 
 // One Ahrens-Dieter GS attempt for the class at position i of the small-alpha list, as straight-line
 // code (no branches, so the attempts of a lane's cursors interleave in the pipelines).  Works in
@@ -125,7 +129,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   extern __shared__ __align__(16) unsigned char k2_smem[];
   const int C = p.C, T = p.n_samples;
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
-  float* wbase = reinterpret_cast<float*>(img_pref + 1040) + (size_t)(threadIdx.x >> 5) * k2_warp_floats(C);
+  float* wbase = reinterpret_cast<float*>(img_pref + k2_pref_ints(p.B)) + (size_t)(threadIdx.x >> 5) * k2_warp_floats(C);
   float4* cst4 = reinterpret_cast<float4*>(wbase);            // [C]
   unsigned* lbuf = reinterpret_cast<unsigned*>(wbase + 4 * C);   // [C][17 words] = [C][34] bf16
   float* s_alpha = wbase + 4 * C + C * (kLStride / 2);        // [C]
@@ -164,8 +168,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
     g = __shfl_sync(full, g, 0);
     if (g >= items) break;
     const int gp = SPLIT ? g % total : g;                    // pair (index over the whole launch)
-    const int sub0 = SPLIT ? g / total : 0;                  // first sub-range of this item
-    const int sub1 = SPLIT ? sub0 + 1 : kK2Sub;
+    const int sub0 = SPLIT ? g / total : 0;                  // the sub-range of this item (split form)
     g = gp;
     // locate (image, pair) by binary search in the prefix
     int lo = 0, hi = p.B;
@@ -236,12 +239,23 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       // ---- free-running sampler (log2 units throughout) ----
       const unsigned gid = image_ids ? (unsigned)image_ids[b] : (unsigned)b;
       const unsigned pid = (unsigned)row | ((unsigned)obj << 20);
-      for (int sub = sub0; sub < sub1; ++sub) {
+      // one flat loop over the rounds of this item; the per-pair form folds the running sub-range into
+      // the totals whenever a sub-range boundary (multiple of sub_len) is crossed
       for (int c = lane; c < C; c += 32) s_part[c] = 0.f;
       float ent_sub = 0.f;
       __syncwarp();
-      const int t_end = min(T, (sub + 1) * sub_len);
-      for (int t0 = sub * sub_len; t0 < t_end; t0 += 32) {
+      const int t_end = SPLIT ? min(T, (sub0 + 1) * sub_len) : T;
+      int fold_at = sub_len;
+      for (int t0 = SPLIT ? sub0 * sub_len : 0; t0 < t_end; t0 += 32) {
+        if (!SPLIT && t0 == fold_at) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ent_sub += __shfl_xor_sync(full, ent_sub, o);
+          ent_acc += ent_sub;
+          ent_sub = 0.f;
+          for (int c = lane; c < C; c += 32) { s_avg[c] += s_part[c]; s_part[c] = 0.f; }
+          fold_at += sub_len;
+          __syncwarp();
+        }
         const int t = t0 + lane;
         const bool active = t < T;
         // Normalisation is a log-sum-exp around a reference exponent m fixed BEFORE the draws:
@@ -342,19 +356,18 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         }
         __syncwarp();
       }
-      // close the sub-range: its class sums and entropy sum, combined in sub-range order
+      // close the (last) sub-range: its class sums and entropy sum, combined in sub-range order
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ent_sub += __shfl_xor_sync(full, ent_sub, o);
       if constexpr (!SPLIT) {
         for (int c = lane; c < C; c += 32) s_avg[c] += s_part[c];
         ent_acc += ent_sub;
       } else {
-        float* dst = part + ((size_t)gp * kK2Sub + sub) * (C + 1);
+        float* dst = part + ((size_t)gp * kK2Sub + sub0) * (C + 1);
         for (int c = lane; c < C; c += 32) __stcg(dst + c, s_part[c]);
         if (lane == 0) __stcg(dst + C, ent_sub);
       }
       __syncwarp();
-      }
       if constexpr (SPLIT) {
         // the last of the pair's kK2Sub items to arrive combines the partial sums (in sub-range order)
         __threadfence();

@@ -344,7 +344,7 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
       !o->pair_unc)
     return arg_fail("null K2 buffer");
   if (p.C > 256) return arg_fail("c_out must be <= 256 for the K2 class lists");
-  const size_t smem = k2_smem_bytes(p.C);
+  const size_t smem = k2_smem_bytes(p.C, p.B);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K2 shared-memory layout");
   if (int rc = ensure_dyn_smem(k2_dirichlet_kernel<false>, smem)) return rc;
   if (int rc = ensure_dyn_smem(k2_dirichlet_kernel<true>, smem)) return rc;
