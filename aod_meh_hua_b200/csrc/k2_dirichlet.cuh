@@ -38,7 +38,8 @@ constexpr float kInvE = 0.36787944117144233f;
 // sizes of 2 and 8 images) - kK2Sub warps take one each and the last to finish combines them, so a
 // score does not depend on the batch it was computed in.
 constexpr int kK2Sub = 4;
-constexpr int kK2SplitPairs = 8192;                  // launches with at most this many pairs are split
+constexpr int kK2SplitPairs = 8192;                  // launches with at most this many pairs are split ...
+constexpr int kK2SplitMaxBatch = 64;                 // ... when the batch is small enough for that to be likely
 __host__ __device__ inline size_t k2_part_floats(int C) { return (size_t)kK2SplitPairs * kK2Sub * ((size_t)C + 1); }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -125,7 +126,8 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
                     const int* __restrict__ pair_off, const long long* __restrict__ image_ids,
                     const float* __restrict__ inj, const long long* __restrict__ inj_off,
                     float* __restrict__ pair_unc, int* __restrict__ work_counter,
-                    float* __restrict__ part, int* __restrict__ done, unsigned* __restrict__ status) {
+                    float* __restrict__ part, int* __restrict__ done, const int allow_split,
+                    unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k2_smem[];
   const int C = p.C, T = p.n_samples;
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
@@ -157,7 +159,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   // sub-ranges of the sample index: whole rounds of 32, kK2Sub of them
   const int sub_len = (((T + 31) / 32 + kK2Sub - 1) / kK2Sub) * 32;
   // few pairs and no injected samples: one work item per (pair, sub-range) instead of per pair
-  const bool split_regime = (inj == nullptr && total <= kK2SplitPairs);
+  const bool split_regime = (allow_split != 0 && inj == nullptr && total <= kK2SplitPairs);
   if (split_regime != SPLIT) return;
   constexpr int nsplit = SPLIT ? kK2Sub : 1;
   const int items = total * nsplit;

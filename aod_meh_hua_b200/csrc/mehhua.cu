@@ -369,17 +369,18 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
   const long long* ids = reinterpret_cast<const long long*>(image_ids);
   const long long* ioff = reinterpret_cast<const long long*>(inj_off);
   const int grid = sm_count() * blocks_per_sm;
-  // the pair count lives on the device: both regimes are launched, the one that does not apply returns
-  // at once.  Injected samples (tests) always take the per-pair form.
+  // the pair count lives on the device: for small batches both regimes are launched and the one that
+  // does not apply returns at once.  Large batches and injected samples (tests) take the per-pair form.
+  const int allow_split = (inj == nullptr && p.B <= kK2SplitMaxBatch) ? 1 : 0;
   k2_dirichlet_kernel<false><<<grid, kK2Threads, smem, st>>>(
       p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off, ids, inj, ioff,
-      o->pair_unc, ws.work_counter, ws.k2_part, ws.k2_done, ws.status);
+      o->pair_unc, ws.work_counter, ws.k2_part, ws.k2_done, allow_split, ws.status);
   LAUNCHED("k2_dirichlet_kernel");
-  if (inj == nullptr) {
+  if (allow_split) {
     CU(cudaMemsetAsync(ws.k2_done, 0, (size_t)kK2SplitPairs * sizeof(int), st));
     k2_dirichlet_kernel<true><<<grid, kK2Threads, smem, st>>>(
         p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off, ids, inj, ioff,
-        o->pair_unc, ws.work_counter + 1, ws.k2_part, ws.k2_done, ws.status);
+        o->pair_unc, ws.work_counter + 1, ws.k2_part, ws.k2_done, allow_split, ws.status);
     LAUNCHED("k2_dirichlet_kernel(split)");
   }
   return 0;

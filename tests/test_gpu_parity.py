@@ -447,3 +447,22 @@ def test_scores_do_not_depend_on_the_batch_they_were_computed_in():
             n = int(r.pair_off[j, -1])
             assert np.array_equal(r.pair_unc[j, :n].cpu().numpy(), unc_big[lo + j])
         assert np.array_equal(r.image_scores.cpu().numpy(), want[sl])
+
+
+def test_scores_do_not_depend_on_the_batch_large_batch_few_pairs():
+    """Batches above 64 images always take the per-pair form of K2, even with few pairs; the same
+    images in batches of 7 take the split form.  Bit-identical scores either way."""
+    spec, batch = make_batch("tiny_retina_coco", list(range(70)))
+    params = ScoringParams(n_samples=500)
+    big = Scorer(spec, params, max_batch=70, device="cuda:0")
+    res = big.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                    batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    assert 0 < int(res.pair_off[:, -1].sum()) <= 8192
+    want = res.image_scores.cpu().numpy().copy()
+    small = Scorer(spec, params, max_batch=7, device="cuda:0")
+    for lo in range(0, 70, 7):
+        sl = slice(lo, lo + 7)
+        r = small.score([t[sl] for t in batch["cls_scores"]], [t[sl] for t in batch["bbox_preds"]],
+                        [t[sl] for t in batch["L_scores"]], batch["anchors"], batch["img_shapes"][sl],
+                        batch["scale_factors"][sl], image_ids=batch["gids"][sl])
+        assert np.array_equal(r.image_scores.cpu().numpy(), want[sl])
