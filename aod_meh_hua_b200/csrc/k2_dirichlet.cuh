@@ -71,9 +71,11 @@ __device__ __forceinline__ void sts_bf16(unsigned a, float v) {      // round-to
 __device__ __forceinline__ unsigned lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // per-warp shared memory, in floats:
-//   cst4[C] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*17 words] | alpha[C] | avg[C] | part[C] | lists 3 x C bytes
+//   cst4[C+4] (float4: b, 1/alpha, alpha-1, -b; in small-list order) | lbuf[C*17 words] | alpha[C] | avg[C] | part[C] |
+//   lists 3 x (C+4) bytes.  The small list and its constants carry 4 benign pad entries, so a cursor that has
+//   run past the end (by at most 3) still reads valid memory and needs no clamp.
 __host__ __device__ inline size_t k2_warp_floats(int C) {
-  const size_t f = 4 * (size_t)C + (size_t)C * (kLStride / 2) + 3 * (size_t)C + (3 * (size_t)C + 3) / 4;
+  const size_t f = 4 * ((size_t)C + 4) + (size_t)C * (kLStride / 2) + 3 * (size_t)C + (3 * ((size_t)C + 4) + 3) / 4;
   return (f + 3) & ~(size_t)3;
 }
 // + the per-image pair-count prefix [B+1], padded to 16 ints
@@ -91,7 +93,7 @@ __host__ __device__ inline size_t k2_smem_bytes(int C, int B) {
 __device__ __forceinline__ bool gs_attempt(const int i, const int nsmall, const float f0, const float f1,
                                            const unsigned s_small, const unsigned s_cst4, unsigned& c, float& l2) {
   // f0, f1 in [1,2): U1 = f0 - 1 = (k + 1/2) / 2^16, U2 = f1 - 1 + 2^-17 in (0,1) (16-bit each)
-  const unsigned ii = (unsigned)min(i, nsmall - 1);
+  const unsigned ii = (unsigned)i;                      // <= nsmall + 3: pad entries
   c = lds_u8(s_small + ii);
   const float4 k = lds_v4(s_cst4 + ii * 16u);           // b, 1/alpha, alpha-1, -b (list order)
   const float pp = fmaf(f0, k.x, k.w);                  // b * U1
@@ -133,13 +135,13 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
   int* img_pref = reinterpret_cast<int*>(k2_smem);            // [B+1] exclusive prefix of pair counts
   float* wbase = reinterpret_cast<float*>(img_pref + k2_pref_ints(p.B)) + (size_t)(threadIdx.x >> 5) * k2_warp_floats(C);
   float4* cst4 = reinterpret_cast<float4*>(wbase);            // [C]
-  unsigned* lbuf = reinterpret_cast<unsigned*>(wbase + 4 * C);   // [C][17 words] = [C][34] bf16
-  float* s_alpha = wbase + 4 * C + C * (kLStride / 2);        // [C]
+  unsigned* lbuf = reinterpret_cast<unsigned*>(wbase + 4 * (C + 4));   // [C][17 words] = [C][34] bf16
+  float* s_alpha = wbase + 4 * (C + 4) + C * (kLStride / 2);  // [C]
   float* s_avg = s_alpha + C;                                 // [C]
   float* s_part = s_avg + C;                                  // [C] class sums of the current sub-range
   unsigned char* s_small = reinterpret_cast<unsigned char*>(s_part + C);
-  unsigned char* s_big = s_small + C;
-  unsigned char* s_bad = s_big + C;
+  unsigned char* s_big = s_small + C + 4;
+  unsigned char* s_bad = s_big + C + 4;
   const int lane = threadIdx.x & 31;
   const unsigned a_cst4 = (unsigned)__cvta_generic_to_shared(cst4);
   const unsigned a_small = (unsigned)__cvta_generic_to_shared(s_small);
@@ -211,6 +213,10 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
         s_alpha[c] = bad ? 0.f : a;
         s_avg[c] = 0.f;
       }
+    }
+    if (lane < 4) {       // pad entries read by finished cursors (their attempts are discarded)
+      s_small[nsmall + lane] = 0;
+      cst4[nsmall + lane] = make_float4(1.f, 1.f, 0.f, -1.f);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(full, amax, o));
@@ -316,8 +322,8 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
             const bool okb = gs_attempt(ib, nsmall, f0[1], f1[1], a_small, a_cst4, cb, lb);
             const bool okc = gs_attempt(ic, nsmall, f0[2], f1[2], a_small, a_cst4, cc, lc);
             const bool okd = gs_attempt(id, nsmall, f0[3], f1[3], a_small, a_cst4, cd, ld);
-            const float da = fmaxf(la - m, -300.f), db = fmaxf(lb - m, -300.f);
-            const float dc = fmaxf(lc - m, -300.f), dd = fmaxf(ld - m, -300.f);
+            // l is finite (U1 > 0, alpha >= 1e-30), so d = l - m needs no clamp: e = 0 below 2^-149 and 0 * d = 0
+            const float da = la - m, db = lb - m, dc = lc - m, dd = ld - m;
             const float ea = ex2_approx(da), eb = ex2_approx(db), ec = ex2_approx(dc), ed = ex2_approx(dd);
             if (oka) { sts_bf16(a_lrow + ca * (kLStride * 2u), ea); asum += ea; bs = fmaf(ea, da, bs); ia += 4; }
             if (okb) { sts_bf16(a_lrow + cb * (kLStride * 2u), eb); asum += eb; bs = fmaf(eb, db, bs); ib += 4; }
