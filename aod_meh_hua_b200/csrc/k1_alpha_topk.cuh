@@ -310,11 +310,10 @@ __device__ __forceinline__ void k1_flush_rows(const float* tile /* warp's [32][s
   const int lane = threadIdx.x & 31;
   const unsigned long long mine = reinterpret_cast<unsigned long long>(srow);
   __syncwarp();
-#pragma unroll 4
-  for (int i = 0; i < 32; ++i) {
-    const unsigned long long d = __shfl_sync(full, mine, i);
-    if (d == 0ull) continue;                       // warp-uniform: lane i has no row
-    float* dst = reinterpret_cast<float*>(d);
+  // only the lanes that hold a row (all of them in the gather kernel, a few in the rescan kernel)
+  for (unsigned m = __ballot_sync(full, mine != 0ull); m != 0u; m &= m - 1u) {
+    const int i = __ffs(m) - 1;
+    float* dst = reinterpret_cast<float*>(__shfl_sync(full, mine, i));
     const float* src = tile + i * K1Tile<C>::stride;
     for (int c = lane; c < C; c += 32) dst[c] = src[c];
   }
