@@ -58,8 +58,6 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ float u24(unsigned w) { return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f; }
 
 // shared-memory accessors on 32-bit shared-window addresses (keeps address arithmetic in one IMAD)
-__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
 __device__ __forceinline__ float4 lds_v4(unsigned a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
