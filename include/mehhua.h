@@ -168,7 +168,10 @@ int mehhua_iou_pairs(const mehhua_config_t* cfg, const mehhua_level_t* levels, i
  * image_ids [B] (device, may be NULL = 0..B-1) key the Philox streams by global image id.
  * inj_samples (may be NULL): the oracle's drawn samples, one [T, P_bs, C_out] block per
  * (image, level) at element offset inj_off[b*S + s] (device int64, -1 = no block); when given
- * the kernel consumes them instead of drawing. */
+ * the kernel consumes them instead of drawing.
+ * Free-running results are a pure function of (seed, image id, row, object, alpha row, T): they do
+ * not depend on the batch, the launch geometry or the world size (the T samples are accumulated in
+ * four fixed sub-ranges combined in order, whether one warp or four work on a pair). */
 int mehhua_k2_dirichlet_epi(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
                             const int64_t* image_ids, const float* inj_samples,
                             const int64_t* inj_off, const mehhua_buffers_t* out, void* workspace,
