@@ -180,3 +180,19 @@ def test_oracle_max_conf_matches_reference():
         per_img, per_lvl = O.get_max_conf(batch["cls_scores"], spec.c_out)
         assert np.array_equal(per_lvl.numpy(), g[f"maxconf_levels_{name}"])
         assert np.array_equal(np.asarray(per_img, dtype=np.float64), g[f"maxconf_{name}"])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port of the reference path) needs no GPU and prints
+    one JSON line with the keys the driver reads."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
+                          "tiny_retina_coco", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 2 and line["gpu_launches"] == 0
+    assert line["config"]["workload"] == "tiny_retina_coco"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
