@@ -357,13 +357,35 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
 }
 
 // ------------------------------------------------------------------------------------------
-// K1c (rescan form): levels where most priors are kept (no top-k at all, or k >= N/8) are walked
-// a second time with K1a's coalesced tiling; a prior finds its row arithmetically (no top-k:
+// Same flush for rows that sit anywhere in the block's tile: lane i's scores are at tile_row_i.
+template <int C>
+__device__ __forceinline__ void k1_flush_rows_at(const float* my_tile_row, float* srow) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long dst_mine = reinterpret_cast<unsigned long long>(srow);
+  const unsigned long long src_mine = reinterpret_cast<unsigned long long>(my_tile_row);
+  __syncwarp();
+  for (unsigned m = __ballot_sync(full, dst_mine != 0ull); m != 0u; m &= m - 1u) {
+    const int i = __ffs(m) - 1;
+    float* dst = reinterpret_cast<float*>(__shfl_sync(full, dst_mine, i));
+    const float* src = reinterpret_cast<const float*>(__shfl_sync(full, src_mine, i));
+    for (int c = lane; c < C; c += 32) dst[c] = src[c];
+  }
+  __syncwarp();
+}
+
+// K1c (rescan form): levels where many priors are kept (no top-k at all, or 2k >= N) are walked a
+// second time with K1a's coalesced tiling; a prior finds its row arithmetically (no top-k:
 // row = k_off + n) or through the inverse map K1b scattered (row or -1).  Traffic = the level's
-// logits once more, instead of 8x that for a sector-granular gather.
+// logits once more, instead of ~25x the kept rows for a sector-granular gather.
+// Two phases per 128-position tile: (1) every thread loads its C logits (full coalesced lines, as in
+// K1a) and the kept ones park them in their row of the shared-memory tile and join a list;
+// (2) the listed rows are handed out to the first threads of the block, so the row arithmetic
+// (softmax, argmax, box decode, candidates) runs once per KEPT row, not once per warp that happens
+// to hold one.
 // ------------------------------------------------------------------------------------------
 template <int C, int HEAD>
-__global__ void __launch_bounds__(kK1aThreads)
+__global__ void __launch_bounds__(kK1aThreads, 4)
 k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
                   const float* __restrict__ scale_factors, const int* __restrict__ inv_map,
                   int* __restrict__ topk_idx, float* __restrict__ score_rows, float* __restrict__ lam_rows,
@@ -380,30 +402,75 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
   const LevelDev& L = p.lv[s];
   const int lt = ti - L.rtile0;
   const int a = lt / L.tpp;
-  const int hw = (lt - a * L.tpp) * kK1aThreads + threadIdx.x;
+  const int hw0 = (lt - a * L.tpp) * kK1aThreads;
+  const int hw = hw0 + threadIdx.x;
   int ncand = 0, r = -1;
   float bmax = 0.f;
   float* srow = nullptr;
   __shared__ float tile[(C > 0) ? (kK1aThreads * K1Tile<C>::stride) : 1];
-  float* tile_row = (C > 0) ? tile + threadIdx.x * K1Tile<C>::stride : nullptr;
-  if (hw < L.HW) {
-    const int n = hw * L.A + a;
-    float x[C > 0 ? C : 1];
-    k1_load_logits<C>(L, b, a, hw, x);      // every thread loads: full coalesced lines, as in K1a
-    if (L.topk) {
-      r = inv_map[(size_t)b * p.N + L.n_off + a * L.HW + hw];
-    } else {
-      r = L.k_off + n;
-      topk_idx[(size_t)b * p.K + r] = n;
+  if constexpr (C == 0) {
+    // generic class count: rows are recomputed by streaming from global memory, one thread per prior
+    float* tile_row = nullptr;
+    if (hw < L.HW) {
+      const int n = hw * L.A + a;
+      float x[1];
+      if (L.topk) {
+        r = inv_map[(size_t)b * p.N + L.n_off + a * L.HW + hw];
+      } else {
+        r = L.k_off + n;
+        topk_idx[(size_t)b * p.K + r] = n;
+      }
+      if (r >= 0) {
+        tile_row = score_rows + ((size_t)b * p.K + r) * p.C;
+        k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
+                             row_argmax, x, tile_row, ncand, bmax, srow);
+      }
     }
-    if (r >= 0) {
-      if (C == 0) tile_row = score_rows + ((size_t)b * p.K + r) * p.C;
+    k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
+  } else {
+    __shared__ int s_cnt;
+    __shared__ short s_lane[kK1aThreads];      // position inside the tile of each kept prior
+    __shared__ int s_row[kK1aThreads];         // its output row
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (hw < L.HW) {
+      float x[C];
+      k1_load_logits<C>(L, b, a, hw, x);      // every thread loads: full coalesced lines, as in K1a
+      if (L.topk) {
+        r = inv_map[(size_t)b * p.N + L.n_off + a * L.HW + hw];
+      } else {
+        r = L.k_off + hw * L.A + a;
+        topk_idx[(size_t)b * p.K + r] = hw * L.A + a;
+      }
+      if (r >= 0) {
+        float* mine = tile + threadIdx.x * K1Tile<C>::stride;
+#pragma unroll
+        for (int c = 0; c < C; ++c) mine[c] = x[c];
+        const int pos = atomicAdd(&s_cnt, 1);
+        s_lane[pos] = (short)threadIdx.x;
+        s_row[pos] = r;
+      }
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    r = -1;
+    float* tile_row = nullptr;
+    if ((int)threadIdx.x < cnt) {
+      const int src = s_lane[threadIdx.x];
+      r = s_row[threadIdx.x];
+      tile_row = tile + src * K1Tile<C>::stride;
+      float x[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) x[c] = tile_row[c];
+      const int n = (hw0 + src) * L.A + a;
       k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
                            row_argmax, x, tile_row, ncand, bmax, srow);
     }
+    if (cnt > (int)(threadIdx.x & ~31)) {      // warp-uniform: this warp holds rows
+      k1_flush_rows_at<C>(tile_row, srow);
+      k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
+    }
   }
-  if constexpr (C > 0) k1_flush_rows<C>(tile + (threadIdx.x & ~31) * K1Tile<C>::stride, srow);
-  k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
 }
 
 }  // namespace mehhua

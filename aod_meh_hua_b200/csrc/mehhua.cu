@@ -20,6 +20,11 @@
 
 using namespace mehhua;
 
+// a level's kept rows come from the coalesced rescan instead of the gather when RATIO * k >= n
+#ifndef MEHHUA_RESCAN_RATIO
+#define MEHHUA_RESCAN_RATIO 2
+#endif
+
 namespace {
 
 thread_local char g_err[256] = "";
@@ -96,7 +101,7 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
     L.tile0 = (int)tile0;
     // rows of a level come from the coalesced rescan when many priors are kept: the gather touches one
     // 32-byte sector (64-byte DRAM burst) per 4-byte logit, i.e. 8-16x the bytes it needs
-    L.rescan = (!L.topk || 2ll * L.k >= n) ? 1 : 0;
+    L.rescan = (!L.topk || (long long)MEHHUA_RESCAN_RATIO * L.k >= n) ? 1 : 0;
     L.rtile0 = (int)rtile0;
     if (L.rescan) rtile0 += (long long)L.tpp * L.A;
     n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
