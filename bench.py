@@ -232,8 +232,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     img_bytes = 4 * spec.num_priors * (spec.c_out + 5)
-    B = args.batch or max(1, min(256, int(17.6e9 // img_bytes)))      # <= 17.6 GB of head outputs per step
-    ring = args.ring or max(2 * B, ((int(35.2e9 // img_bytes)) // B) * B)
+    # images per step: at most 3 x 148 (three waves of the one-block-per-image kernels on the B200's 148 SMs)
+    # and at most 30 GB of head outputs per step (cfg 3: 437 images); ring = 2..4 steps of distinct images
+    B = args.batch or max(1, min(444, int(30e9 // img_bytes)))
+    ring = args.ring or max(2 * B, ((int(60e9 // img_bytes)) // B) * B)
     ring = max(B, (min(ring, 4 * B) // B) * B)
     pool_size = POOL_SIZES.get(spec.name, 100000)
     lo, hi = shard_range(pool_size, rank, world)
