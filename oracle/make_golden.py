@@ -39,6 +39,13 @@ CASES = [
 ]
 
 
+VARIANT_CASES = [
+    # the ablation head Lambda_L2Net_ReLU: thresholds from kwargs (Lambda_L2_ReLU.py:150-154, 397-400),
+    # alpha = score row without lambda' (:425-427).  name, spec, ids, pool seed, sample seed, score_thr, iou_thr
+    ("relu_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 77, 0.4, 0.6),
+]
+
+
 ALL_CASES = [
     # name, spec, image ids, pool seed, sample seed, aggregation type
     ("all_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 5, "scaleAvg_classAvg"),
@@ -54,10 +61,10 @@ def batch_checksum(batch) -> str:
     return h.hexdigest()
 
 
-def run_reference_case(spec_name, gids, pool_seed, sample_seed, sf, upool2, clsw):
+def run_reference_case(spec_name, gids, pool_seed, sample_seed, sf, upool2, clsw, kind=None, score_thr=0.3, iou_thr=0.9):
     spec = get_spec(spec_name)
     batch = SyntheticPool(spec, seed0=pool_seed, scale_factor=sf).batch(gids)
-    kind = "retina" if spec.head == HEAD_RETINA else "ssd"
+    kind = kind or ("retina" if spec.head == HEAD_RETINA else "ssd")
     head = RL.make_head(kind, spec.c_out, spec.target_stds, spec.score_thr, spec.max_per_img, spec.nms_pre,
                         spec.nms_iou)
     rec = []
@@ -83,8 +90,8 @@ def run_reference_case(spec_name, gids, pool_seed, sample_seed, sf, upool2, clsw
 
     head.ComputeObjUnc = compute_spy
     kw = dict(isUnc="Epistemic", uPool="Entropy_NMS", uPool2=upool2, L_scores=batch["L_scores"], isEval=False,
-              showNMS=False, saveUnc=False, saveMaxConf=False, clsW=clsw, scaleUnc=False, score_thr=0.3,
-              iou_thr=0.9, batchIdx=0, return_box=False)
+              showNMS=False, saveUnc=False, saveMaxConf=False, clsW=clsw, scaleUnc=False, score_thr=score_thr,
+              iou_thr=iou_thr, batchIdx=0, return_box=False)
     torch.manual_seed(sample_seed)
     dets, unc = head._get_bboxes(batch["cls_scores"], batch["bbox_preds"], batch["anchors"], batch["img_shapes"],
                                  [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]], None, True, True,
@@ -242,6 +249,12 @@ def main():
     only_kats = "--only-kats" in sys.argv
     for name, spec_name, gids, pseed, sseed, sf, up2, clsw in ([] if only_kats else CASES):
         g = run_reference_case(spec_name, gids, pseed, sseed, sf, up2, clsw)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **g)
+        print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")
+    for name, spec_name, gids, pseed, sseed, thr, iou in ([] if only_kats or "--skip-variants" in sys.argv else VARIANT_CASES):
+        g = run_reference_case(spec_name, gids, pseed, sseed, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False,
+                               kind="retina_relu", score_thr=thr, iou_thr=iou)
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")

@@ -107,13 +107,16 @@ def base_namespace() -> Dict[str, object]:
 def make_head(kind: str, c_out: int, stds, score_thr: float, max_per_img: int, nms_pre: int = 1000,
               nms_iou: float = 0.5, ns: Dict[str, object] = None):
     """A stub `self` carrying the reference's real _get_bboxes / ComputeObjUnc /
-    AggregateObjScaleUnc bound as methods.  kind: 'retina' (Lambda_L2Net) | 'ssd' (MyLSSDHead)."""
+    AggregateObjScaleUnc bound as methods.  kind: 'retina' (Lambda_L2Net) | 'ssd' (MyLSSDHead) |
+    'retina_relu' (Lambda_L2Net_ReLU, Lambda_L2_ReLU.py:146-276, 395-444)."""
     ns = dict(base_namespace() if ns is None else ns)
     if kind == "retina":
         rel, cls, act = "mmdet/models/dense_heads/Lambda_L2.py", "Lambda_L2Net", "relu"
     elif kind == "ssd":
         rel, cls, act = "mmdet/models/dense_heads/My_L_ssd_head.py", "MyLSSDHead", "softmax"
         ns["ignoreBG"] = False          # My_L_ssd_head.py:19
+    elif kind == "retina_relu":         # ablation head: thresholds from kwargs, alpha = scores (no lambda')
+        rel, cls, act = "mmdet/models/dense_heads/Lambda_L2_ReLU.py", "Lambda_L2Net_ReLU", "relu"
     else:
         raise ValueError(kind)
     names = ["_get_bboxes", "ComputeObjUnc", "AggregateObjScaleUnc", "ComputeScaleUnc",

@@ -11,7 +11,7 @@ from aod_meh_hua_b200 import anchors as A
 from aod_meh_hua_b200.specs import ScoringParams, get_spec, parse_agg_spec
 from aod_meh_hua_b200.synth import SyntheticPool
 from oracle import meh_hua_oracle as O
-from oracle.make_golden import ALL_CASES, CASES, batch_checksum
+from oracle.make_golden import ALL_CASES, CASES, VARIANT_CASES, batch_checksum
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -20,9 +20,24 @@ def _load(name):
     return np.load(os.path.join(GOLD, f"{name}.npz"))
 
 
+@pytest.mark.parametrize("case", VARIANT_CASES, ids=[c[0] for c in VARIANT_CASES])
+def test_ablation_head_parameters_match_the_reference_variant(case):
+    """Lambda_L2Net_ReLU (Lambda_L2_ReLU.py:146-276, 395-444): thresholds from kwargs drive the object
+    filter, the cluster IoU and both foreground tests, and alpha is the score row without lambda'.
+    The restatement with ScoringParams(fg_thr = obj_thr = score_thr, cluster_iou = iou_thr,
+    use_lambda = False) reproduces the variant head's own outputs."""
+    name, spec_name, gids, pseed, sseed, thr, iou = case
+    _check_against_golden(name, spec_name, gids, pseed, sseed, (1.0, 1.0, 1.0, 1.0),
+                          ScoringParams(fg_thr=thr, obj_thr=thr, cluster_iou=iou, use_lambda=False))
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_restatement_matches_reference_outputs(case):
     name, spec_name, gids, pseed, sseed, sf, up2, clsw = case
+    _check_against_golden(name, spec_name, gids, pseed, sseed, sf, ScoringParams(agg=up2, cls_w=clsw))
+
+
+def _check_against_golden(name, spec_name, gids, pseed, sseed, sf, params):
     g = _load(name)
     spec = get_spec(spec_name)
     batch = SyntheticPool(spec, seed0=pseed, scale_factor=sf).batch(gids)
@@ -35,7 +50,6 @@ def test_restatement_matches_reference_outputs(case):
         return smp
 
     torch.manual_seed(sseed)
-    params = ScoringParams(agg=up2, cls_w=clsw)
     out = O.score_batch(batch, sampler=sampler, **O.spec_kwargs(spec, params))
     # detections and cluster membership: bit-exact
     for b in range(len(gids)):
