@@ -196,3 +196,30 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["config"]["workload"] == "tiny_retina_coco"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_ctypes_structs_follow_the_header_field_for_field():
+    """The ctypes mirrors in _lib.py must list the fields of mehhua_level_t / mehhua_config_t /
+    mehhua_buffers_t in the header's order (an ABI drift would silently shift every pointer)."""
+    hdr = open(os.path.join(ROOT, "include", "mehhua.h")).read()
+
+    def fields(struct_name):
+        body = re.search(r"typedef struct " + struct_name + r"\s*\{(.*?)\}\s*\w+;", hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):          # `int32_t H, W, A;` declares three fields
+                m = re.search(r"(\w+)\s*(\[\d+\])?$", part.strip())
+                names.append(m.group(1))
+        return names
+
+    assert fields("mehhua_buffers") == list(_lib.BUFFER_FIELDS)
+    assert fields("mehhua_config") == [f[0] for f in _lib.Config._fields_]
+    # the level struct calls the MEH map `lambda` in C and `lam` in Python (keyword)
+    assert [n if n != "lambda" else "lam" for n in fields("mehhua_level")] == [f[0] for f in _lib.Level._fields_]
+    assert C.sizeof(_lib.Buffers) == 8 * len(_lib.BUFFER_FIELDS)
+    ver = int(re.search(r"#define MEHHUA_ABI_VERSION (\d+)", hdr).group(1))
+    assert ver == _lib.ABI_VERSION
