@@ -276,20 +276,41 @@ def calculate_uncertainty(cfg, model, data_loader, **kwargs):
     return [x.cpu() for x in out]
 
 
+# The reference's scoring heads and how their scoring methods relate to Lambda_L2Net's (compared by
+# AST: `_get_bboxes`, `ComputeObjUnc`, `AggregateObjScaleUnc`, `ComputeScaleUnc`, `AggregateScaleUnc`):
+#   identical text   : Lambda_L1Net (Lambda_L1.py), Lambda_MSLENet (Lambda_MSLE.py),
+#                      Lambda_L2Net_reverse (Lambda_L2_reverseorder.py)
+#   kwargs thresholds: Lambda_L2Net_ablation (Lambda_L2_ablation.py:  score_thr / iou_thr from kwargs, lambda' kept)
+#   kwargs thresholds, alpha = score row (no lambda'): Lambda_L2Net_NoL (Lambda_L2_noL.py), Lambda_L2Net_ReLU
+HEAD_VARIANTS = {
+    # registered name: (module, class, thresholds from kwargs, use_lambda)
+    "Lambda_L2Net_B200": ("Lambda_L2", "Lambda_L2Net", False, True),
+    "Lambda_L1Net_B200": ("Lambda_L1", "Lambda_L1Net", False, True),
+    "Lambda_MSLENet_B200": ("Lambda_MSLE", "Lambda_MSLENet", False, True),
+    "Lambda_L2Net_reverse_B200": ("Lambda_L2_reverseorder", "Lambda_L2Net_reverse", False, True),
+    "Lambda_L2Net_ablation_B200": ("Lambda_L2_ablation", "Lambda_L2Net_ablation", True, True),
+    "Lambda_L2Net_NoL_B200": ("Lambda_L2_noL", "Lambda_L2Net_NoL", True, False),
+    "Lambda_L2Net_ReLU_B200": ("Lambda_L2_ReLU", "Lambda_L2Net_ReLU", True, False),
+    "MyLSSDHead_B200": ("My_L_ssd_head", "MyLSSDHead", False, True),
+}
+
+
+def make_variant(name: str, base: type) -> type:
+    """The B200 drop-in class for one of the reference's scoring heads (`base` = the reference class)."""
+    _, _, from_kwargs, use_lambda = HEAD_VARIANTS[name]
+    return type(name, (B200ScoringMixin, base), dict(
+        mehhua_thresholds_from_kwargs=from_kwargs, mehhua_params=ScoringParams(use_lambda=use_lambda)))
+
+
 def register_heads():
-    """Register `Lambda_L2Net_B200` / `MyLSSDHead_B200` with the reference's HEADS registry (needs
+    """Register the `*_B200` drop-in heads (HEAD_VARIANTS) with the reference's HEADS registry (needs
     the reference's mmdet + mmcv importable).  Select with `--bbox-head Lambda_L2Net_B200`
-    (tools/train_RetinaNet.py:59,90) or `bbox_head=dict(type='Lambda_L2Net_B200', ...)`."""
+    (tools/train_RetinaNet.py:59,90) or `bbox_head=dict(type='Lambda_L2Net_B200', ...)`.
+    Returns the registered classes by name."""
+    import importlib
     from mmdet.models.builder import HEADS
-    from mmdet.models.dense_heads.Lambda_L2 import Lambda_L2Net
-    from mmdet.models.dense_heads.My_L_ssd_head import MyLSSDHead
-
-    @HEADS.register_module()
-    class Lambda_L2Net_B200(B200ScoringMixin, Lambda_L2Net):
-        pass
-
-    @HEADS.register_module()
-    class MyLSSDHead_B200(B200ScoringMixin, MyLSSDHead):
-        pass
-
-    return Lambda_L2Net_B200, MyLSSDHead_B200
+    out = {}
+    for name, (module, cls, _, _) in HEAD_VARIANTS.items():
+        base = getattr(importlib.import_module(f"mmdet.models.dense_heads.{module}"), cls)
+        out[name] = HEADS.register_module()(make_variant(name, base))
+    return out

@@ -223,3 +223,27 @@ def test_ctypes_structs_follow_the_header_field_for_field():
     assert C.sizeof(_lib.Buffers) == 8 * len(_lib.BUFFER_FIELDS)
     ver = int(re.search(r"#define MEHHUA_ABI_VERSION (\d+)", hdr).group(1))
     assert ver == _lib.ABI_VERSION
+
+
+def test_head_variants_cover_the_reference_scoring_heads():
+    """HEAD_VARIANTS: one drop-in class per scoring head of the reference, with the two switches that
+    distinguish their scoring methods (thresholds from kwargs, lambda' scaling)."""
+    from aod_meh_hua_b200.dropin import HEAD_VARIANTS, B200ScoringMixin, make_variant
+
+    class Base:
+        def _get_bboxes(self, *a, **k):
+            return "reference"
+
+    want = {"Lambda_L2Net_B200": (False, True), "Lambda_L1Net_B200": (False, True), "Lambda_MSLENet_B200": (False, True),
+            "Lambda_L2Net_reverse_B200": (False, True), "Lambda_L2Net_ablation_B200": (True, True),
+            "Lambda_L2Net_NoL_B200": (True, False), "Lambda_L2Net_ReLU_B200": (True, False),
+            "MyLSSDHead_B200": (False, True)}
+    assert {k: v[2:] for k, v in HEAD_VARIANTS.items()} == want
+    for name in HEAD_VARIANTS:
+        cls = make_variant(name, Base)
+        assert cls.__name__ == name and issubclass(cls, B200ScoringMixin) and issubclass(cls, Base)
+        assert cls.mehhua_thresholds_from_kwargs == want[name][0]
+        assert cls.mehhua_params.use_lambda == want[name][1]
+        # non-scoring routes fall through to the reference method
+        assert cls()._get_bboxes([torch.zeros(1, 9, 2, 2)], [], [], [(8, 8, 3)], [], None, False, False,
+                                 isUnc="Epistemic", uPool="Entropy_NoNMS") == "reference"
