@@ -41,8 +41,10 @@ CASES = [
 
 VARIANT_CASES = [
     # the ablation head Lambda_L2Net_ReLU: thresholds from kwargs (Lambda_L2_ReLU.py:150-154, 397-400),
-    # alpha = score row without lambda' (:425-427).  name, spec, ids, pool seed, sample seed, score_thr, iou_thr
-    ("relu_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 77, 0.4, 0.6),
+    # alpha = score row without lambda' (:425-427); Lambda_L2Net_ablation: the same thresholds with lambda' kept.
+    # name, spec, ids, pool seed, sample seed, score_thr, iou_thr, head kind, use_lambda
+    ("relu_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 77, 0.4, 0.6, "retina_relu", False),
+    ("ablation_retina_voc", "tiny_retina_voc", [0, 1], 20, 78, 0.35, 0.9, "retina_ablation", True),
 ]
 
 
@@ -252,9 +254,9 @@ def main():
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")
-    for name, spec_name, gids, pseed, sseed, thr, iou in ([] if only_kats or "--skip-variants" in sys.argv else VARIANT_CASES):
+    for name, spec_name, gids, pseed, sseed, thr, iou, kind, _ in ([] if only_kats or "--skip-variants" in sys.argv else VARIANT_CASES):
         g = run_reference_case(spec_name, gids, pseed, sseed, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False,
-                               kind="retina_relu", score_thr=thr, iou_thr=iou)
+                               kind=kind, score_thr=thr, iou_thr=iou)
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")

@@ -22,13 +22,14 @@ def _load(name):
 
 @pytest.mark.parametrize("case", VARIANT_CASES, ids=[c[0] for c in VARIANT_CASES])
 def test_ablation_head_parameters_match_the_reference_variant(case):
-    """Lambda_L2Net_ReLU (Lambda_L2_ReLU.py:146-276, 395-444): thresholds from kwargs drive the object
-    filter, the cluster IoU and both foreground tests, and alpha is the score row without lambda'.
-    The restatement with ScoringParams(fg_thr = obj_thr = score_thr, cluster_iou = iou_thr,
-    use_lambda = False) reproduces the variant head's own outputs."""
-    name, spec_name, gids, pseed, sseed, thr, iou = case
+    """Lambda_L2Net_ReLU (Lambda_L2_ReLU.py:146-276, 395-444) and Lambda_L2Net_ablation
+    (Lambda_L2_ablation.py): thresholds from kwargs drive the object filter, the cluster IoU and both
+    foreground tests; the ReLU head's alpha is the score row without lambda'.  The restatement with
+    ScoringParams(fg_thr = obj_thr = score_thr, cluster_iou = iou_thr, use_lambda = ...) reproduces
+    the variant heads' own outputs."""
+    name, spec_name, gids, pseed, sseed, thr, iou, _, use_lambda = case
     _check_against_golden(name, spec_name, gids, pseed, sseed, (1.0, 1.0, 1.0, 1.0),
-                          ScoringParams(fg_thr=thr, obj_thr=thr, cluster_iou=iou, use_lambda=False))
+                          ScoringParams(fg_thr=thr, obj_thr=thr, cluster_iou=iou, use_lambda=use_lambda))
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
