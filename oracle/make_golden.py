@@ -54,6 +54,11 @@ ALL_CASES = [
     ("all_ssd_voc", "tiny_ssd_voc", [0, 1, 2], 20, 5, "scaleSum_classAvg"),
 ]
 
+ALL_VARIANT_CASES = [
+    # Entropy_ALL route of Lambda_L2Net_NoL (alpha = softmax, no lambda'): name, spec, ids, seeds, type, head kind
+    ("all_nol_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 6, "scaleSum_classSum", "retina_nol"),
+]
+
 
 def batch_checksum(batch) -> str:
     h = hashlib.sha256()
@@ -125,12 +130,12 @@ def run_reference_case(spec_name, gids, pool_seed, sample_seed, sf, upool2, clsw
     return g
 
 
-def run_reference_all_case(spec_name, gids, pool_seed, sample_seed, kind):
+def run_reference_all_case(spec_name, gids, pool_seed, sample_seed, kind, head_kind=None):
     """Entropy_ALL route of the reference's _get_bboxes (with_nms=False) -> ComputeScaleUnc ->
     AggregateScaleUnc, all four aggregation types on the same draws."""
     spec = get_spec(spec_name)
     batch = SyntheticPool(spec, seed0=pool_seed).batch(gids)
-    head = RL.make_head("retina" if spec.head == HEAD_RETINA else "ssd", spec.c_out, spec.target_stds,
+    head = RL.make_head(head_kind or ("retina" if spec.head == HEAD_RETINA else "ssd"), spec.c_out, spec.target_stds,
                         spec.score_thr, spec.max_per_img, spec.nms_pre, spec.nms_iou)
     g = dict(checksum=np.frombuffer(bytes.fromhex(batch_checksum(batch)), dtype=np.uint8))
     captured = {}
@@ -262,6 +267,11 @@ def main():
         print(f"{path}: scores {g['image_scores']}, {os.path.getsize(path)} bytes")
     for name, spec_name, gids, pseed, sseed, kind in ([] if only_kats else ALL_CASES):
         g = run_reference_all_case(spec_name, gids, pseed, sseed, kind)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **g)
+        print(f"{path}: {g['scores_' + kind]}, {os.path.getsize(path)} bytes")
+    for name, spec_name, gids, pseed, sseed, kind, head_kind in ([] if only_kats else ALL_VARIANT_CASES):
+        g = run_reference_all_case(spec_name, gids, pseed, sseed, kind, head_kind)
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: {g['scores_' + kind]}, {os.path.getsize(path)} bytes")

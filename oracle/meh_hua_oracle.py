@@ -351,9 +351,10 @@ def aggregate_obj_scale_unc(nested, spec: str, cls_w: bool = False) -> List[floa
 # --------------------------------------------------------------------------------------------
 def compute_scale_unc(cls_scores: List[torch.Tensor], L_scores: List[torch.Tensor], *, head: int, c_out: int,
                       T: int = 500, fg_thr: float = 0.3, lambda_scale: float = 25.0, lambda_eps: float = 1e-7,
-                      sampler: SampleFn = default_sampler):
+                      use_lambda: bool = True, sampler: SampleFn = default_sampler):
     """Every prior with max softmax > fg_thr is sampled; no NMS / objects.  Returns (nested, flat):
-    nested[i][s][str(cls)] = (ale, epi) as the reference builds it."""
+    nested[i][s][str(cls)] = (ale, epi) as the reference builds it.  use_lambda=False is the
+    Lambda_L2Net_NoL / Lambda_L2Net_ReLU form (alpha = softmax, Lambda_L2_noL.py ComputeScaleUnc)."""
     S = len(cls_scores)
     B = cls_scores[0].shape[0]
     nested = [[{} for _ in range(S)] for _ in range(B)]
@@ -368,7 +369,7 @@ def compute_scale_unc(cls_scores: List[torch.Tensor], L_scores: List[torch.Tenso
                 continue
             lam = L_scores[s][i].permute(1, 2, 0).reshape(-1, 1)
             lam_p = lam.mean() / (lam + lambda_eps) * lambda_scale
-            alpha = (p * lam_p)[fg]
+            alpha = (p * lam_p)[fg] if use_lambda else p[fg]
             smp = sampler(alpha, T, i, s)
             total, ale, epi = uncertainty_from_samples(smp)
             pcls = alpha.argmax(dim=1)
@@ -401,9 +402,10 @@ def aggregate_scale_unc(nested, kind: str):
 
 def score_batch_all(batch: Dict[str, object], *, head: int, c_out: int, T: int = 500, fg_thr: float = 0.3,
                     lambda_scale: float = 25.0, lambda_eps: float = 1e-7, kind: str = "scaleAvg_classAvg",
-                    sampler: SampleFn = default_sampler, **_unused) -> Dict[str, object]:
+                    use_lambda: bool = True, sampler: SampleFn = default_sampler, **_unused) -> Dict[str, object]:
     nested, flat = compute_scale_unc(batch["cls_scores"], batch["L_scores"], head=head, c_out=c_out, T=T,
-                                     fg_thr=fg_thr, lambda_scale=lambda_scale, lambda_eps=lambda_eps, sampler=sampler)
+                                     fg_thr=fg_thr, lambda_scale=lambda_scale, lambda_eps=lambda_eps,
+                                     use_lambda=use_lambda, sampler=sampler)
     return dict(nested=nested, flat=flat, image_scores=aggregate_scale_unc(nested, kind))
 
 

@@ -117,6 +117,8 @@ def make_head(kind: str, c_out: int, stds, score_thr: float, max_per_img: int, n
         ns["ignoreBG"] = False          # My_L_ssd_head.py:19
     elif kind == "retina_relu":         # ablation head: thresholds from kwargs, alpha = scores (no lambda')
         rel, cls, act = "mmdet/models/dense_heads/Lambda_L2_ReLU.py", "Lambda_L2Net_ReLU", "relu"
+    elif kind == "retina_nol":          # Lambda_L2Net_NoL: thresholds from kwargs, alpha = scores (no lambda')
+        rel, cls, act = "mmdet/models/dense_heads/Lambda_L2_noL.py", "Lambda_L2Net_NoL", "relu"
     elif kind == "retina_ablation":     # ablation head: thresholds from kwargs, lambda' kept
         rel, cls, act = "mmdet/models/dense_heads/Lambda_L2_ablation.py", "Lambda_L2Net_ablation", "relu"
     else:

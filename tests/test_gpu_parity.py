@@ -466,3 +466,36 @@ def test_scores_do_not_depend_on_the_batch_large_batch_few_pairs():
                         [t[sl] for t in batch["L_scores"]], batch["anchors"], batch["img_shapes"][sl],
                         batch["scale_factors"][sl], image_ids=batch["gids"][sl])
         assert np.array_equal(r.image_scores.cpu().numpy(), want[sl])
+
+
+def test_entropy_all_without_lambda_matches_the_nol_head():
+    """Entropy_ALL route of Lambda_L2Net_NoL / _ReLU (alpha = softmax row, no lambda'): the oracle form
+    is pinned against the reference head's own output (tests/golden/all_nol_retina_coco.npz); here the
+    kernels against that oracle with its samples injected."""
+    from oracle import meh_hua_oracle as O
+    from tests.helpers import Recorder
+    kind = "scaleSum_classSum"
+    spec, batch = make_batch("tiny_retina_coco", [0, 1, 2])
+    params = ScoringParams(agg=kind, use_lambda=False)
+    rec = Recorder(6)
+    out = O.score_batch_all(batch, kind=kind, sampler=rec, **O.spec_kwargs(spec, params))
+    sc = Scorer(spec, params, max_batch=3, device="cuda:0", mode="all")
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    sc.all_rows()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off)
+    sc.hua()
+    torch.cuda.synchronize()
+    res = sc.result()
+    poff = res.pair_off.cpu().numpy()
+    for b in range(B):
+        for r in [r for r in out["flat"] if r["image"] == b]:
+            a, e = poff[b, r["level"]], poff[b, r["level"] + 1]
+            assert np.array_equal(res.topk_idx[b, a:e].cpu().numpy(), r["prior"])
+            np.testing.assert_allclose(res.score_rows[b, a:e].cpu().numpy(), r["alpha"], rtol=2e-5, atol=1e-12)
+            unc = res.pair_unc[b, a:e].cpu().numpy()
+            np.testing.assert_allclose(unc[:, 1], r["ale"], rtol=RTOL, atol=2e-6)
+            np.testing.assert_allclose(unc[:, 2], r["epi"], rtol=1e-4, atol=5e-6)
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float64),
+                               rtol=RTOL, atol=1e-5)

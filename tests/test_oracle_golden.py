@@ -11,7 +11,7 @@ from aod_meh_hua_b200 import anchors as A
 from aod_meh_hua_b200.specs import ScoringParams, get_spec, parse_agg_spec
 from aod_meh_hua_b200.synth import SyntheticPool
 from oracle import meh_hua_oracle as O
-from oracle.make_golden import ALL_CASES, CASES, VARIANT_CASES, batch_checksum
+from oracle.make_golden import ALL_CASES, ALL_VARIANT_CASES, CASES, VARIANT_CASES, batch_checksum
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -81,16 +81,17 @@ def _check_against_golden(name, spec_name, gids, pseed, sseed, sf, params):
         np.testing.assert_allclose(np.asarray(out["image_scores"]), g["image_scores"], rtol=0.1)
 
 
-@pytest.mark.parametrize("case", ALL_CASES, ids=[c[0] for c in ALL_CASES])
+@pytest.mark.parametrize("case", [c + (None,) for c in ALL_CASES] + ALL_VARIANT_CASES, ids=lambda c: c[0])
 def test_entropy_all_restatement_matches_reference_outputs(case):
-    name, spec_name, gids, pseed, sseed, kind = case
+    name, spec_name, gids, pseed, sseed, kind, head_kind = case
+    use_lambda = head_kind != "retina_nol"
     g = _load(name)
     spec = get_spec(spec_name)
     batch = SyntheticPool(spec, seed0=pseed).batch(gids)
     assert bytes.fromhex(batch_checksum(batch)) == g["checksum"].tobytes(), "synthetic inputs drifted"
     for typ in ("scaleAvg_classAvg", "scaleSum_classSum", "scaleSum_classAvg", "scaleAvg_classSum"):
         torch.manual_seed(sseed)
-        out = O.score_batch_all(batch, kind=typ, **O.spec_kwargs(spec, ScoringParams()))
+        out = O.score_batch_all(batch, kind=typ, **O.spec_kwargs(spec, ScoringParams(use_lambda=use_lambda)))
         groups = np.asarray([(b, s, int(c), float(ale), float(epi)) for b, img in enumerate(out["nested"])
                              for s, lvl in enumerate(img) for c, (ale, epi) in lvl.items()], dtype=np.float64).reshape(-1, 5)
         assert np.array_equal(groups[:, :3], g["groups"][:, :3])          # (image, level, class) keys: exact
