@@ -247,3 +247,23 @@ def test_head_variants_cover_the_reference_scoring_heads():
         # non-scoring routes fall through to the reference method
         assert cls()._get_bboxes([torch.zeros(1, 9, 2, 2)], [], [], [(8, 8, 3)], [], None, False, False,
                                  isUnc="Epistemic", uPool="Entropy_NoNMS") == "reference"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mehhua.h is a C header (C99, no C++ constructs): a C translation unit that includes it
+    compiles with gcc -pedantic and links against the shared library."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "mehhua.h"\n#include <stdio.h>\n'
+                   'int main(void) { mehhua_config_t c; mehhua_buffers_t b; (void)c; (void)b;\n'
+                   '  printf("%d %d %d\\n", mehhua_abi_version(), (int)sizeof(mehhua_level_t), (int)sizeof(mehhua_buffers_t));\n'
+                   '  return mehhua_abi_version() == MEHHUA_ABI_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    lib_dir = os.path.join(ROOT, "aod_meh_hua_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", lib_dir, "-lmehhua", f"-Wl,-rpath,{lib_dir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    ver, lvl, bufs = (int(v) for v in run.stdout.split())
+    assert ver == _lib.ABI_VERSION and lvl == C.sizeof(_lib.Level) and bufs == C.sizeof(_lib.Buffers)
