@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmehhua.so")
 MAX_LEVELS = 8
 MAX_DETS = 256
 MAX_NMS_PRE = 4096
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
 ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA = 1, 2, 4
@@ -45,7 +45,7 @@ class Config(C.Structure):
 
 BUFFER_FIELDS = ["score_rows", "lam_rows", "boxes", "topk_idx", "row_max", "row_argmax", "level_fg",
                  "dets", "det_labels", "det_flat", "n_det", "n_obj", "pair_row", "pair_obj",
-                 "pair_cls", "pair_off", "lam_mean", "pair_unc", "image_scores", "level_maxconf"]
+                 "pair_cls", "pair_off", "lam_mean", "pair_unc", "image_scores", "level_maxconf", "pair_avg"]
 
 
 class Buffers(C.Structure):
@@ -84,26 +84,39 @@ SYMBOLS = {
 }
 
 _lib = None
+_variants = {}
+# A/B build of the same sources with fp32 (instead of bfloat16) staging of K2's draws; tests only
+FP32_STAGE_LIB_PATH = os.path.join(_HERE, "libmehhua_fp32stage.so")
 
 
-def load() -> C.CDLL:
-    """Load libmehhua.so (once).  Raises MehhuaError when it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.isfile(LIB_PATH):
+def _open(path: str) -> C.CDLL:
+    if not os.path.isfile(path):
         raise MehhuaError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "or `make -C aod_meh_hua_b200/csrc` - there is no CPU fallback for the scoring path")
-    lib = C.CDLL(LIB_PATH)
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C aod_meh_hua_b200/csrc all` - there is no CPU fallback for the scoring path")
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
     if lib.mehhua_abi_version() != ABI_VERSION:
-        raise MehhuaError(f"libmehhua ABI {lib.mehhua_abi_version()} != binding ABI {ABI_VERSION}")
-    _lib = lib
+        raise MehhuaError(f"{os.path.basename(path)} ABI {lib.mehhua_abi_version()} != binding ABI {ABI_VERSION}")
     return lib
+
+
+def load() -> C.CDLL:
+    """Load libmehhua.so (once).  Raises MehhuaError when it has not been built."""
+    global _lib
+    if _lib is None:
+        _lib = _open(LIB_PATH)
+    return _lib
+
+
+def load_variant(path: str) -> C.CDLL:
+    """Load another build of the library (same ABI), e.g. FP32_STAGE_LIB_PATH."""
+    if path not in _variants:
+        _variants[path] = _open(path)
+    return _variants[path]
 
 
 def check(rc: int, what: str) -> None:

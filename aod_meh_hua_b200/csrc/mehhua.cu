@@ -74,7 +74,7 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   if (cfg->nms_pre > MEHHUA_MAX_NMS_PRE) return arg_fail("nms_pre must be <= 4096");
   if (B < 1 || B > 1024) return arg_fail("batch must be 1..1024");
   if (cfg->pair_cap < 1) return arg_fail("pair_cap must be positive");
-  if (cfg->n_samples < 1) return arg_fail("n_samples must be positive");
+  if (cfg->n_samples < 0) return arg_fail("n_samples must be >= 0 (0 = analytic form)");
   if (cfg->mode != MEHHUA_MODE_NMS && cfg->mode != MEHHUA_MODE_ALL) return arg_fail("mode");
   for (int a : {cfg->agg_object, cfg->agg_scale, cfg->agg_class})
     if (a < MEHHUA_AGG_SUM || a > MEHHUA_AGG_MAX) return arg_fail("aggregation op");
@@ -376,16 +376,16 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
   const int grid = sm_count() * blocks_per_sm;
   // the pair count lives on the device: for small batches both regimes are launched and the one that
   // does not apply returns at once.  Large batches and injected samples (tests) take the per-pair form.
-  const int allow_split = (inj == nullptr && p.B <= kK2SplitMaxBatch) ? 1 : 0;
+  const int allow_split = (inj == nullptr && p.n_samples > 0 && p.B <= kK2SplitMaxBatch) ? 1 : 0;
   k2_dirichlet_kernel<false><<<grid, kK2Threads, smem, st>>>(
       p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off, ids, inj, ioff,
-      o->pair_unc, ws.work_counter, ws.k2_part, ws.k2_done, allow_split, ws.status);
+      o->pair_unc, o->pair_avg, ws.work_counter, ws.k2_part, ws.k2_done, allow_split, ws.status);
   LAUNCHED("k2_dirichlet_kernel");
   if (allow_split) {
     CU(cudaMemsetAsync(ws.k2_done, 0, (size_t)kK2SplitPairs * sizeof(int), st));
     k2_dirichlet_kernel<true><<<grid, kK2Threads, smem, st>>>(
         p, o->score_rows, o->lam_rows, o->lam_mean, o->pair_row, o->pair_obj, o->pair_off, ids, inj, ioff,
-        o->pair_unc, ws.work_counter + 1, ws.k2_part, ws.k2_done, allow_split, ws.status);
+        o->pair_unc, o->pair_avg, ws.work_counter + 1, ws.k2_part, ws.k2_done, allow_split, ws.status);
     LAUNCHED("k2_dirichlet_kernel(split)");
   }
   return 0;
@@ -680,6 +680,7 @@ int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* lev
   b.lam_mean = reinterpret_cast<float*>(a + o_lm);      b.pair_unc = reinterpret_cast<float*>(a + o_pu);
   b.image_scores = reinterpret_cast<float*>(a + o_sc);
   b.level_maxconf = nullptr;               // getMaxConf is not part of the host-buffer call
+  b.pair_avg = nullptr;
   c->img_shapes = reinterpret_cast<float*>(a + o_shp);
   c->scale_factors = reinterpret_cast<float*>(a + o_sf);
   c->image_ids = reinterpret_cast<int64_t*>(a + o_ids);

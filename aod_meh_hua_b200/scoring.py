@@ -77,11 +77,12 @@ class Scorer:
     """Device-resident buffers + kernel launches for one detector geometry."""
 
     def __init__(self, spec: DetectorSpec, params: Optional[ScoringParams] = None, max_batch: int = 8,
-                 device="cuda:0", pair_cap: Optional[int] = None, rescale: bool = True, mode: str = "nms"):
+                 device="cuda:0", pair_cap: Optional[int] = None, rescale: bool = True, mode: str = "nms", lib=None):
         """mode 'nms' = the Entropy_NMS route (objects from NMS, HUA over object/scale/class);
         mode 'all' = the Entropy_ALL route (every foreground prior, params.agg is one of the four
-        'scaleX_classY' types, row buffers hold up to pair_cap foreground priors per image)."""
-        self.lib = _lib.load()
+        'scaleX_classY' types, row buffers hold up to pair_cap foreground priors per image).
+        lib: an alternative build of the library (tests: the fp32-staging A/B build)."""
+        self.lib = lib or _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MehhuaError("the MEH/HUA scoring path needs a CUDA device (sm_100a); none is visible")
         self.spec = spec
@@ -116,8 +117,10 @@ class Scorer:
             image_scores=torch.zeros(B, **f32), level_maxconf=torch.zeros(B, S, **f32))
         self.bufs = _lib.Buffers()
         for name in _lib.BUFFER_FIELDS:
-            setattr(self.bufs, name, self.t[name].data_ptr())
+            if name in self.t:
+                setattr(self.bufs, name, self.t[name].data_ptr())
         self.bufs.level_maxconf = None          # optional output, off unless save_max_conf(True)
+        self.bufs.pair_avg = None               # diagnostic output of K2, off unless save_pair_avg(True)
         self.ws_bytes = int(self.lib.mehhua_workspace_bytes(C.byref(self.cfg), self._shape_levels, B))
         if self.ws_bytes == 0:
             _lib.check(_lib.E_ARG, "mehhua_workspace_bytes")
@@ -133,6 +136,14 @@ class Scorer:
         """Ask the logits pass to also produce getMaxConf's per-level maxima (utils/functions.py:467-476;
         the reference computes them only under saveMaxConf).  Off by default."""
         self.bufs.level_maxconf = self.t["level_maxconf"].data_ptr() if on else None
+
+    def save_pair_avg(self, on: bool = True) -> None:
+        """Ask K2 to also write mean_t x_c of every pair (`avg` of Lambda_L2.py:521) into
+        `self.t['pair_avg']` [B, pair_cap, C_out] - a diagnostic for the per-class moment tests."""
+        if on and "pair_avg" not in self.t:
+            self.t["pair_avg"] = torch.zeros(self.max_batch, self.pair_cap, self.spec.c_out, dtype=torch.float32,
+                                             device=self.device)
+        self.bufs.pair_avg = self.t["pair_avg"].data_ptr() if on else None
 
     # ------------------------------------------------------------------ inputs
     def _stream(self) -> int:
@@ -274,7 +285,7 @@ class Scorer:
 
     def result(self) -> BatchResult:
         B = self._B
-        return BatchResult(B=B, **{k: v[:B] for k, v in self.t.items()})
+        return BatchResult(B=B, **{k: v[:B] for k, v in self.t.items() if k != "pair_avg"})
 
     # ------------------------------------------------------------------ whole path
     def score(self, cls_scores, bbox_preds, L_scores, anchors, img_shapes, scale_factors, image_ids=None,
@@ -309,12 +320,14 @@ def pool_topk(scores: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None)
 
 
 def pair_uncertainty(rows: torch.Tensor, lam: torch.Tensor, pair_row: torch.Tensor, pair_obj: torch.Tensor,
-                     params: ScoringParams, seed_ids=(0, 0), inj_samples: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     params: ScoringParams, seed_ids=(0, 0), inj_samples: Optional[torch.Tensor] = None,
+                     return_avg: bool = False, lib=None):
     """K2 on an explicit pair list of ONE (image, level): rows [K, C] scores, lam [K], pair_row /
     pair_obj [P] -> [P, 3] (total, aleatoric, epistemic).  Used by the ComputeObjUnc compatibility
     method, whose cluster masks come from the caller.  lambda' = mean(lam[pair_row]) / (lam + eps)
-    * scale as in Lambda_L2.py:513-515."""
-    lib = _lib.load()
+    * scale as in Lambda_L2.py:513-515.  return_avg: also the class means mean_t x_c [P, C]
+    (Lambda_L2.py:521 `avg`).  lib: an alternative build of the library (tests: the fp32-staging A/B build)."""
+    lib = lib or _lib.load()
     if not rows.is_cuda:
         raise _lib.MehhuaError("pair_uncertainty needs CUDA tensors; there is no CPU fallback")
     dev = rows.device
@@ -341,6 +354,10 @@ def pair_uncertainty(rows: torch.Tensor, lam: torch.Tensor, pair_row: torch.Tens
     bufs = _lib.Buffers()
     bufs.score_rows, bufs.lam_rows, bufs.lam_mean = rows.data_ptr(), lam.data_ptr(), lmean.data_ptr()
     bufs.pair_row, bufs.pair_obj, bufs.pair_off, bufs.pair_unc = prow.data_ptr(), pobj.data_ptr(), poff.data_ptr(), unc.data_ptr()
+    avg = None
+    if return_avg:
+        avg = torch.zeros(max(P, 1), Cc, device=dev)
+        bufs.pair_avg = avg.data_ptr()
     ws_bytes = int(lib.mehhua_workspace_bytes(C.byref(cfg), lv, 1))
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
     ids = torch.tensor([int(seed_ids[0]) * 64 + int(seed_ids[1])], dtype=torch.int64, device=dev)
@@ -354,4 +371,6 @@ def pair_uncertainty(rows: torch.Tensor, lam: torch.Tensor, pair_row: torch.Tens
         _lib.check(lib.mehhua_k2_dirichlet_epi(C.byref(cfg), lv, 1, ids.data_ptr(), ip, io, C.byref(bufs),
                                                ws.data_ptr(), ws_bytes, st), "mehhua_k2_dirichlet_epi")
         torch.cuda.current_stream(dev).synchronize()
+    if return_avg:
+        return unc[:P], avg[:P]
     return unc[:P]

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MEHHUA_ABI_VERSION 2
+#define MEHHUA_ABI_VERSION 3
 #define MEHHUA_MAX_LEVELS 8
 #define MEHHUA_MAX_DETS 256      /* upper bound on max_per_img */
 #define MEHHUA_MAX_NMS_PRE 4096  /* upper bound on nms_pre */
@@ -85,7 +85,9 @@ typedef struct mehhua_config {
   float   lambda_scale;    /* 25   Lambda_L2.py:515 */
   float   lambda_eps;      /* 1e-7 Lambda_L2.py:514 */
   int32_t use_lambda;      /* 1; 0 = Lambda_L2_noL.py:531 */
-  int32_t n_samples;       /* 500  Lambda_L2.py:520 */
+  int32_t n_samples;       /* 500  Lambda_L2.py:520; 0 = analytic form (T -> infinity: total = H(alpha/alpha0),
+                              aleatoric = psi(alpha0+1) - sum (alpha_c/alpha0) psi(alpha_c+1)), a deterministic
+                              mode for set-identity tests - not a reference mode */
   int32_t agg_object, agg_scale, agg_class;  /* MEHHUA_AGG_*; 'objectSum_scaleMax_classSum' */
   int32_t cls_w;           /* clsW: multiply by the number of distinct classes (Lambda_L2.py:617) */
   float   means[4];        /* bbox_coder target_means */
@@ -121,6 +123,8 @@ typedef struct mehhua_buffers {
   float*   level_maxconf;/* [B, S] or NULL     max over ALL priors of max_c softmax: the `output`   *
                           *                    of getMaxConf (utils/functions.py:467-476); fused   *
                           *                    into the logits pass (K1a / KA1), NULL = skipped     */
+  float*   pair_avg;     /* [B, pair_cap, C_out] or NULL: mean_t x_c of every pair (`avg` of Lambda_L2.py:521),  *
+                          *                    a diagnostic output of K2 for the per-class moment tests     */
 } mehhua_buffers_t;
 
 int         mehhua_abi_version(void);
