@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmehhua.so")
 MAX_LEVELS = 8
 MAX_DETS = 256
 MAX_NMS_PRE = 4096
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
 ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA = 1, 2, 4
@@ -85,8 +85,9 @@ SYMBOLS = {
 
 _lib = None
 _variants = {}
-# A/B build of the same sources with fp32 (instead of bfloat16) staging of K2's draws; tests only
-FP32_STAGE_LIB_PATH = os.path.join(_HERE, "libmehhua_fp32stage.so")
+# A/B builds of the same sources (`make -C aod_meh_hua_b200/csrc variants`; experiments and tests only)
+BF16_STAGE_LIB_PATH = os.path.join(_HERE, "libmehhua_bf16stage.so")    # K2 stages its draws as bfloat16
+PHILOX10_LIB_PATH = os.path.join(_HERE, "libmehhua_philox10.so")        # K2's sampler runs Philox4x32-10
 
 
 def _open(path: str) -> C.CDLL:
@@ -108,12 +109,12 @@ def load() -> C.CDLL:
     """Load libmehhua.so (once).  Raises MehhuaError when it has not been built."""
     global _lib
     if _lib is None:
-        _lib = _open(LIB_PATH)
+        _lib = _open(os.environ.get("MEHHUA_LIB", LIB_PATH))     # MEHHUA_LIB: an A/B build, for experiments
     return _lib
 
 
 def load_variant(path: str) -> C.CDLL:
-    """Load another build of the library (same ABI), e.g. FP32_STAGE_LIB_PATH."""
+    """Load another build of the library (same ABI), e.g. PHILOX10_LIB_PATH."""
     if path not in _variants:
         _variants[path] = _open(path)
     return _variants[path]

@@ -581,15 +581,15 @@ int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int
   return 0;
 }
 
-// debug / known-answer entry for the Philox block (tests only): out = 4 host uint32
-int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+// debug / known-answer entry for the Philox block (tests only): out = 8 host uint32 (10 rounds, then 7)
+int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[8]) {
   int rc = check_device();
   if (rc) return rc;
   unsigned* d = nullptr;
-  CU(cudaMalloc(&d, 16));
+  CU(cudaMalloc(&d, 32));
   philox_kat_kernel<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
   LAUNCHED("philox_kat_kernel");
-  cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(out, d, 32, cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
   return 0;

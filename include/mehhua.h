@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MEHHUA_ABI_VERSION 3
+#define MEHHUA_ABI_VERSION 4
 #define MEHHUA_MAX_LEVELS 8
 #define MEHHUA_MAX_DETS 256      /* upper bound on max_per_img */
 #define MEHHUA_MAX_NMS_PRE 4096  /* upper bound on nms_pre */
@@ -226,8 +226,9 @@ int    mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, 
                            int64_t* idx_out, int32_t* n_selected_out, void* workspace,
                            size_t workspace_bytes, void* stream);
 
-/* Known-answer hook for the Philox4x32-10 block of K2 (tests): ctr[4], key[2] -> out[4], host arrays. */
-int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* Known-answer hook for the Philox4x32 block of K2 (tests): ctr[4], key[2] -> out[8], host arrays:
+ * out[0..3] = the 10-round block, out[4..7] = the 7-round block (the one K2's sampler uses). */
+int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[8]);
 
 /* Host-buffer entry point: same as mehhua_score_batch but every pointer in `levels`, img_shapes,
  * scale_factors, image_ids and image_scores_host is HOST memory.  The call copies the inputs to

@@ -179,16 +179,19 @@ def test_philox_known_answers():
     import ctypes as C
     from aod_meh_hua_b200 import _lib
     lib = _lib.load()
+    # Random123 kat_vectors, philox4x32 with 10 rounds and with 7 (the variant K2's sampler runs)
     kats = [
-        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
-        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8),
+         (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd),
+         (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662)),
         ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
-         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1), (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)),
     ]
-    for ctr, key, want in kats:
-        out = (C.c_uint32 * 4)()
+    for ctr, key, want10, want7 in kats:
+        out = (C.c_uint32 * 8)()
         _lib.check(lib.mehhua_debug_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out), "philox")
-        assert tuple(out) == want
+        assert tuple(out)[:4] == want10 and tuple(out)[4:] == want7
 
 
 def test_pool_topk_matches_stable_argsort():

@@ -76,7 +76,7 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.MehhuaError):
         pool_topk(torch.rand(10), 3)
     lib = _lib.load()
-    out = (C.c_uint32 * 4)()
+    out = (C.c_uint32 * 8)()
     rc = lib.mehhua_debug_philox((C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0), out)
     assert rc == _lib.E_NODEVICE
 
