@@ -56,20 +56,27 @@
 
 namespace mehhua {
 
-constexpr int kK2Threads = 256;
+#ifndef MEHHUA_K2_THREADS
+#define MEHHUA_K2_THREADS 256
+#endif
+constexpr int kK2Threads = MEHHUA_K2_THREADS;
 constexpr int kK2Warps = kK2Threads / 32;
 #ifdef MEHHUA_K2_STAGE_BF16
 constexpr int kLWords = 17;                           // bf16 staging: 34 halves per class row
 constexpr int kK2MinBlocks = 3;
 #else
 constexpr int kLWords = 33;                           // fp32 staging: 32 samples + 1 pad word per class row
-constexpr int kK2MinBlocks = 2;
+constexpr int kK2MinBlocks = 512 / MEHHUA_K2_THREADS;
 #endif
 constexpr float kFltMin = 1.17549435e-38f;
 constexpr float kGsTiny = 1e-3f;                      // below: the tiny list (threshold compare + full-resolution draws)
 constexpr float kEm2Half = 0.067667641618306351f;     // e^-2 / 2 (tiny list: s = 2)
 constexpr float kEm1 = 0.36787944117144233f;          // e^-1 / 1 (GS list: s = 1)
 constexpr float kTinySpan = 130.f;                    // a p<=1 draw is non-zero only when log2 x - m >= -(kTinySpan - log2 s): 126 + margin
+#ifndef MEHHUA_K2_UNROLL
+#define MEHHUA_K2_UNROLL 2
+#endif
+constexpr int kK2Unroll = MEHHUA_K2_UNROLL;
 constexpr int kQCap = 8;                              // tiny rows a lane can remember having written in one round
 // The T samples of a pair are accumulated in kK2Sub fixed sub-ranges (whole 32-sample rounds) whose
 // partial sums are combined in sub-range order.  The arithmetic is the same whether one warp walks
@@ -272,11 +279,15 @@ __device__ __forceinline__ void k2_draw_sample(const K2Pair& W, const unsigned t
     };
     float4 ka = lds_v4(ca), kb = lds_v4(cb), kc = lds_v4(cc);
     while (__any_sync(full, nxt < done_at)) {
-      const uint4 w = k2_philox(make_uint4(t, kcall++, W.pid, W.gid), W.key);
-      // U2 mantissa bits 22..4 = [9 low bits of the word | 10 bits of w.w]
-      attempt(ca, ka, w.x, (__funnelshift_l(w.w, w.x, 14) & 0x007ffff0u) | W.one);
-      attempt(cb, kb, w.y, (__funnelshift_l(w.w << 10, w.y, 14) & 0x007ffff0u) | W.one);
-      attempt(cc, kc, w.z, (__funnelshift_l(w.w << 20, w.z, 14) & 0x007ffff0u) | W.one);
+      // the "anyone left?" vote is taken once per kK2Unroll Philox blocks
+#pragma unroll
+      for (int rep = 0; rep < kK2Unroll; ++rep) {
+        const uint4 w = k2_philox(make_uint4(t, kcall++, W.pid, W.gid), W.key);
+        // U2 mantissa bits 22..4 = [9 low bits of the word | 10 bits of w.w]
+        attempt(ca, ka, w.x, (__funnelshift_l(w.w, w.x, 14) & 0x007ffff0u) | W.one);
+        attempt(cb, kb, w.y, (__funnelshift_l(w.w << 10, w.y, 14) & 0x007ffff0u) | W.one);
+        attempt(cc, kc, w.z, (__funnelshift_l(w.w << 20, w.z, 14) & 0x007ffff0u) | W.one);
+      }
     }
   }
   // ---- tiny list: four classes per Philox block, one compare each; a hit takes the full formula

@@ -49,12 +49,18 @@ def select_top(uncertainty: torch.Tensor, candidate_mask: Optional[torch.Tensor]
     return pool_topk(uncertainty, n_top, candidate_mask)
 
 
-def update_X_L(uncertainty, X_all, X_L, X_S_size, device="cuda:0", **kwargs):
+def update_X_L(uncertainty, X_all, X_L, X_S_size, device=None, **kwargs):
     """Drop-in for mmdet.utils.active_datasets.update_X_L (:102-135): same arguments, same return
     (sorted X_L_next, X_U_next).  The arg[-n:] part - the global top-k - runs on the GPU; the two
     host-RNG draws (zero-score picks, X_U shuffle) use numpy's global state exactly as the
     reference does.  Ties in the score go to the larger image id (the reference's unstable argsort
-    leaves them unpinned)."""
+    leaves them unpinned).  device: where K4 runs - default: the device of `uncertainty` when it is a
+    CUDA tensor, else the process's current CUDA device (rank r's GPU under torchrun)."""
+    if device is None:
+        if torch.is_tensor(uncertainty) and uncertainty.is_cuda:
+            device = uncertainty.device
+        else:
+            device = torch.device("cuda", torch.cuda.current_device())
     if torch.is_tensor(uncertainty):
         unc_t = uncertainty.detach().float()
         uncertainty = unc_t.cpu().numpy()

@@ -81,7 +81,7 @@ class Scorer:
         """mode 'nms' = the Entropy_NMS route (objects from NMS, HUA over object/scale/class);
         mode 'all' = the Entropy_ALL route (every foreground prior, params.agg is one of the four
         'scaleX_classY' types, row buffers hold up to pair_cap foreground priors per image).
-        lib: an alternative build of the library (tests: the fp32-staging A/B build)."""
+        lib: an alternative build of the library (experiments)."""
         self.lib = lib or _lib.load()
         if not torch.cuda.is_available():
             raise _lib.MehhuaError("the MEH/HUA scoring path needs a CUDA device (sm_100a); none is visible")
@@ -214,6 +214,13 @@ class Scorer:
         self._B = B
 
     # ------------------------------------------------------------------ stages
+    def _call(self, name: str, *args) -> None:
+        """One C-ABI call with the scorer's GPU made current for its duration: the library launches on
+        the current device, which need not be the one the scorer's tensors live on (rank r of a
+        multi-GPU job, or Scorer(device='cuda:1') in a single process)."""
+        with torch.cuda.device(self.device):
+            _lib.check(getattr(self.lib, name)(*args), name)
+
     def _common(self):
         return (C.byref(self.cfg), self._levels, self._B)
 
@@ -221,46 +228,39 @@ class Scorer:
         return (self.workspace.data_ptr(), self.ws_bytes, self._stream())
 
     def k1(self) -> None:
-        _lib.check(self.lib.mehhua_k1_alpha_topk(*self._common(), self._img_shapes.data_ptr(),
-                                                 self._scale_factors.data_ptr(), C.byref(self.bufs),
-                                                 *self._ws()), "mehhua_k1_alpha_topk")
+        self._call("mehhua_k1_alpha_topk", *self._common(), self._img_shapes.data_ptr(),
+                   self._scale_factors.data_ptr(), C.byref(self.bufs), *self._ws())
 
     def nms(self) -> None:
-        _lib.check(self.lib.mehhua_nms_objects(*self._common(), C.byref(self.bufs), *self._ws()),
-                   "mehhua_nms_objects")
+        self._call("mehhua_nms_objects", *self._common(), C.byref(self.bufs), *self._ws())
 
     def pairs(self) -> None:
-        _lib.check(self.lib.mehhua_iou_pairs(*self._common(), C.byref(self.bufs), *self._ws()),
-                   "mehhua_iou_pairs")
+        self._call("mehhua_iou_pairs", *self._common(), C.byref(self.bufs), *self._ws())
 
     def k2(self, inj_samples: Optional[torch.Tensor] = None, inj_off: Optional[torch.Tensor] = None) -> None:
         ids = self._ids.data_ptr() if self._ids is not None else None
         ip = inj_samples.data_ptr() if inj_samples is not None else None
         io = inj_off.data_ptr() if inj_off is not None else None
-        _lib.check(self.lib.mehhua_k2_dirichlet_epi(*self._common(), ids, ip, io, C.byref(self.bufs),
-                                                    *self._ws()), "mehhua_k2_dirichlet_epi")
+        self._call("mehhua_k2_dirichlet_epi", *self._common(), ids, ip, io, C.byref(self.bufs), *self._ws())
 
     def hua(self) -> None:
-        _lib.check(self.lib.mehhua_k3_hua(*self._common(), C.byref(self.bufs), *self._ws()), "mehhua_k3_hua")
+        self._call("mehhua_k3_hua", *self._common(), C.byref(self.bufs), *self._ws())
 
     def all_rows(self) -> None:
-        _lib.check(self.lib.mehhua_all_fg_rows(*self._common(), C.byref(self.bufs), *self._ws()), "mehhua_all_fg_rows")
+        self._call("mehhua_all_fg_rows", *self._common(), C.byref(self.bufs), *self._ws())
 
     def score_bound(self) -> None:
         """The whole path for the bound batch, one C call, no host sync."""
         ids = self._ids.data_ptr() if self._ids is not None else None
         if self.mode == "all":
-            _lib.check(self.lib.mehhua_score_batch_all(*self._common(), ids, C.byref(self.bufs), *self._ws()),
-                       "mehhua_score_batch_all")
+            self._call("mehhua_score_batch_all", *self._common(), ids, C.byref(self.bufs), *self._ws())
             return
-        _lib.check(self.lib.mehhua_score_batch(*self._common(), self._img_shapes.data_ptr(),
-                                               self._scale_factors.data_ptr(), ids, C.byref(self.bufs),
-                                               *self._ws()), "mehhua_score_batch")
+        self._call("mehhua_score_batch", *self._common(), self._img_shapes.data_ptr(),
+                   self._scale_factors.data_ptr(), ids, C.byref(self.bufs), *self._ws())
 
     def read_status(self) -> int:
         st = C.c_uint32(0)
-        _lib.check(self.lib.mehhua_read_status(*self._common(), self.workspace.data_ptr(), self._stream(),
-                                               C.byref(st)), "mehhua_read_status")
+        self._call("mehhua_read_status", *self._common(), self.workspace.data_ptr(), self._stream(), C.byref(st))
         return int(st.value)
 
     def check_status(self) -> int:
@@ -314,8 +314,9 @@ def pool_topk(scores: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None)
         mask = mask.to(device=scores.device, dtype=torch.uint8).contiguous()
         mp = mask.data_ptr()
     st = torch.cuda.current_stream(scores.device).cuda_stream
-    _lib.check(lib.mehhua_k4_pool_topk(scores.data_ptr(), mp, n, k, out.data_ptr(), nsel.data_ptr(),
-                                       ws.data_ptr(), 256, st), "mehhua_k4_pool_topk")
+    with torch.cuda.device(scores.device):       # the library launches on the current device
+        _lib.check(lib.mehhua_k4_pool_topk(scores.data_ptr(), mp, n, k, out.data_ptr(), nsel.data_ptr(),
+                                           ws.data_ptr(), 256, st), "mehhua_k4_pool_topk")
     return out[: int(nsel.item())]
 
 
@@ -326,7 +327,7 @@ def pair_uncertainty(rows: torch.Tensor, lam: torch.Tensor, pair_row: torch.Tens
     pair_obj [P] -> [P, 3] (total, aleatoric, epistemic).  Used by the ComputeObjUnc compatibility
     method, whose cluster masks come from the caller.  lambda' = mean(lam[pair_row]) / (lam + eps)
     * scale as in Lambda_L2.py:513-515.  return_avg: also the class means mean_t x_c [P, C]
-    (Lambda_L2.py:521 `avg`).  lib: an alternative build of the library (tests: the fp32-staging A/B build)."""
+    (Lambda_L2.py:521 `avg`).  lib: an alternative build of the library (experiments)."""
     lib = lib or _lib.load()
     if not rows.is_cuda:
         raise _lib.MehhuaError("pair_uncertainty needs CUDA tensors; there is no CPU fallback")
@@ -368,8 +369,9 @@ def pair_uncertainty(rows: torch.Tensor, lam: torch.Tensor, pair_row: torch.Tens
         ip, io = keep[0].data_ptr(), keep[1].data_ptr()
     st = torch.cuda.current_stream(dev).cuda_stream
     if P:
-        _lib.check(lib.mehhua_k2_dirichlet_epi(C.byref(cfg), lv, 1, ids.data_ptr(), ip, io, C.byref(bufs),
-                                               ws.data_ptr(), ws_bytes, st), "mehhua_k2_dirichlet_epi")
+        with torch.cuda.device(dev):             # the library launches on the current device
+            _lib.check(lib.mehhua_k2_dirichlet_epi(C.byref(cfg), lv, 1, ids.data_ptr(), ip, io, C.byref(bufs),
+                                                   ws.data_ptr(), ws_bytes, st), "mehhua_k2_dirichlet_epi")
         torch.cuda.current_stream(dev).synchronize()
     if return_avg:
         return unc[:P], avg[:P]

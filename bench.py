@@ -5,13 +5,19 @@
 
 A step = one pass of the hot path over one batch of `--batch` synthetic images whose head outputs
 are already resident in HBM (a ring of `--ring` distinct images per GPU, far larger than L2; image
-g uses ring slot g mod ring but its own Philox key g).  `value` = pool images scored per second,
-whole job (all ranks), device-timed with CUDA events, max over ranks; the pool top-k (K4) and, for
-N > 1, the single NCCL all-gather of scores run once inside the timed region.  `e2e` is the same
+g uses ring slot g mod ring but its own Philox key g).  With the default `--steps 0` the timed region
+is ONE PASS OVER THE RANK'S WHOLE SHARD of the pool (cfg 3: 100 000 images, 229 steps of 437 on one
+GPU): every image id of the shard is scored once, its score lands at its own offset, and the pool
+top-k (K4) - after the single NCCL all-gather of scores for N > 1 - selects from real scores.
+`--steps K` times exactly K steps (the first K batches of the shard).  `value` = pool images scored per
+second, whole job (all ranks), device-timed with CUDA events, max over ranks.  `e2e` is the same
 metric through the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).
 `roofline` is for the dominant HBM-streaming kernel K1a (logits -> ranking keys), its duration
-measured live with CUDA events on the launching stream during the timed steps.
-`--impl reference` times the CPU oracle port of the reference's own path on the host cores.
+measured live with CUDA events on the launching stream during the timed steps; `roofline.k2` is the
+sampling stage (time-dominant, compute-bound): live draws/s plus the pipe utilisation of its last ncu
+capture (profiles/k2_pipes.json).
+`--impl reference` times the reference's own CPU path on the host cores: the AST-loaded reference
+functions when /root/reference is mounted (kind "reference"), else the oracle port (kind "port").
 """
 from __future__ import annotations
 
@@ -43,7 +49,7 @@ POOL_SIZES = {"cfg1_retina_r50_512_voc": 16, "cfg2_ssd300_voc": 5000, "cfg3_reti
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (0 = one pass over the rank's whole shard of the pool)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
@@ -53,6 +59,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-batch", type=int, default=32, help="images per host-buffer call")
     ap.add_argument("--cpu-images", type=int, default=4, help="images of the CPU-baseline sample")
+    ap.add_argument("--no-baseline-of-record", action="store_true",
+                    help="skip BASELINE.md section 3's cfg-1 figures (16 images, batch 2, 2 threads and all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager-gpu-images", type=int, default=0,
                     help="also time the oracle port in torch-eager on the GPU over this many images (0 = off)")
@@ -121,20 +129,63 @@ class ClockSampler:
 # CPU reference arm (oracle port of the reference's own path; the reference itself is pure
 # Python on torch and cannot be installed without mmcv - see DESIGN.md)
 # --------------------------------------------------------------------------------------------
-def cpu_reference_rate(spec, params, n_images: int, batch: int, threads: int, seed0: int = 20):
-    from aod_meh_hua_b200.synth import SyntheticPool
+def reference_scorer(spec, params):
+    """(kind, fn): fn(batch) runs the reference's CPU path on one batch of head outputs.
+    kind "reference": the reference's own `_get_bboxes` -> `ComputeObjUnc` -> `AggregateObjScaleUnc`, AST-loaded
+    unmodified from /root/reference (oracle/ref_loader.py; only where that tree is mounted - never on the GPU box);
+    kind "port": the oracle's restatement of the same lines (oracle/meh_hua_oracle.py)."""
+    from aod_meh_hua_b200.specs import HEAD_RETINA
     from oracle import meh_hua_oracle as O
+    try:
+        from oracle import ref_loader as RL
+        have_ref = RL.available()
+    except Exception:
+        have_ref = False
+    if have_ref and params.n_samples == 500 and params.use_lambda:
+        head = RL.make_head("retina" if spec.head == HEAD_RETINA else "ssd", spec.c_out, spec.target_stds,
+                            spec.score_thr, spec.max_per_img, spec.nms_pre, spec.nms_iou)
+
+        def run_ref(batch):
+            kw = dict(isUnc="Epistemic", uPool="Entropy_NMS", uPool2=params.agg, L_scores=batch["L_scores"], isEval=False,
+                      showNMS=False, saveUnc=False, saveMaxConf=False, clsW=params.cls_w, scaleUnc=False, batchIdx=0,
+                      return_box=False)
+            return head._get_bboxes(batch["cls_scores"], batch["bbox_preds"], batch["anchors"], batch["img_shapes"],
+                                    [np.asarray(v, dtype=np.float32) for v in batch["scale_factors"]], None, True, True, **kw)
+        return "reference", run_ref
+    kw = O.spec_kwargs(spec, params)
+    return "port", (lambda batch: O.score_batch(batch, **kw))
+
+
+def cpu_reference_rate(spec, params, n_images: int, batch: int, threads: int, seed0: int = 20):
+    """images/s of the reference's CPU path on `n_images` synthetic images in loader batches of `batch`
+    (one untimed warm-up batch first) with torch.set_num_threads(threads).  Returns (rate, seconds, kind)."""
+    from aod_meh_hua_b200.synth import SyntheticPool
     torch.set_num_threads(threads)
     pool = SyntheticPool(spec, seed0=seed0, device="cpu")
-    kw = O.spec_kwargs(spec, params)
+    kind, fn = reference_scorer(spec, params)
     batches = [pool.batch(list(range(i, min(i + batch, n_images)))) for i in range(0, n_images, batch)]
     torch.manual_seed(20)
-    O.score_batch(pool.batch([n_images]), **kw)          # warm-up batch (not timed)
+    fn(pool.batch([n_images, n_images + 1][:batch]))          # warm-up batch (not timed)
     t0 = time.perf_counter()
     for b in batches:
-        O.score_batch(b, **kw)
+        fn(b)
     dt = time.perf_counter() - t0
-    return n_images / dt, dt
+    return n_images / dt, dt, kind
+
+
+def baseline_of_record(params):
+    """BASELINE.json config 1 as named - 16 synthetic 512x512 images, 20 VOC classes,
+    RetinaNet R50-FPN head shapes, loader batch 2, T = 500 - (i) with torch.set_num_threads(2), the
+    reference's own setting (tools/train_RetinaNet.py:77), and (ii) with all host cores."""
+    from aod_meh_hua_b200.specs import get_spec
+    spec1 = get_spec("cfg1_retina_r50_512_voc")
+    cores = os.cpu_count() or 1
+    out = dict(workload=spec1.name, images=16, batch=2, samples=params.n_samples, os_cpu_count=cores)
+    for label, th in (("threads_2", 2), ("threads_all", cores)):
+        rate, dt, kind = cpu_reference_rate(spec1, params, 16, 2, th)
+        out[label] = dict(value=rate, unit=UNIT, threads=th, seconds=dt)
+        out["kind"] = kind
+    return out
 
 
 def eager_gpu_rate(spec, params, n_images: int, batch: int, device, seed0: int = 20):
@@ -161,32 +212,35 @@ def eager_gpu_rate(spec, params, n_images: int, batch: int, device, seed0: int =
 
 
 def run_reference(args, spec, params, rank):
+    """The reference arm: the reference's own CPU implementation of the path on the host cores, on a bounded
+    sample of the B200 arm's workload (steps of one loader batch of 2 images, the reference's own batch)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     per_step = 2
-    rates = []
     from aod_meh_hua_b200.synth import SyntheticPool
-    from oracle import meh_hua_oracle as O
     torch.set_num_threads(threads)
     pool = SyntheticPool(spec, seed0=20, device="cpu")
-    kw = O.spec_kwargs(spec, params)
+    kind, fn = reference_scorer(spec, params)
     torch.manual_seed(20)
-    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
+    steps = 8 if args.steps <= 0 else max(1, min(args.steps, 8))
+    warm = max(1, min(args.warmup, 1))
     data = [pool.batch([2 * i, 2 * i + 1]) for i in range(2)]
     for i in range(warm):
-        O.score_batch(data[i % 2], **kw)
+        fn(data[i % 2])
     t0 = time.perf_counter()
     for i in range(steps):
-        O.score_batch(data[i % 2], **kw)
+        fn(data[i % 2])
     dt = time.perf_counter() - t0
     value = steps * per_step / dt
-    sample = f"{steps} steps x {per_step} images of {spec.name}, batch 2, T={params.n_samples}, torch CPU"
+    sample = f"{steps} steps x {per_step} images of {spec.name}, batch 2, T={params.n_samples}, torch CPU, {threads} threads"
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(workload=spec.name, samples=params.n_samples, batch=per_step),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    if not args.no_baseline_of_record:
+        line["cpu_baseline"]["baseline_of_record"] = baseline_of_record(params)
     print(json.dumps(line), flush=True)
 
 
@@ -243,25 +297,31 @@ def main():
     sc = Scorer(spec, params, max_batch=B, device=device)
     shp = torch.tensor([[spec.img_hw[0], spec.img_hw[1]]] * B, dtype=torch.float32, device=device)
     sf = torch.ones(B, 4, device=device)
-    pool_scores = torch.zeros(max(hi - lo, B), device=device)
+    n_local = hi - lo
+    pool_scores = torch.zeros(n_local, device=device)
     n_slots = ring // B
     slot_ptrs = []
     for j in range(n_slots):
         slot_ptrs.append([(cls[s][j * B:].data_ptr(), reg[s][j * B:].data_ptr(), lam[s][j * B:].data_ptr(),
                            synth.anchors[s].data_ptr()) for s in range(spec.num_levels)])
-    n_local = hi - lo
-    ids_all = torch.arange(lo, lo + (args.steps + args.warmup + 2) * B, device=device, dtype=torch.int64)
+    steps_per_pass = (n_local + B - 1) // B
+    whole_shard = args.steps <= 0
+    if whole_shard:
+        args.steps = steps_per_pass
+    ids_all = torch.arange(lo, hi, device=device, dtype=torch.int64)
 
     def step(i: int):
+        """Batch i of the shard (wrapping around for --steps beyond one pass): ids, scores at their own offsets."""
         j = i % n_slots
-        ids = ids_all[i * B:(i + 1) * B]
-        sc.bind_raw(slot_ptrs[j], B, shp, sf, ids)
+        a = (i % steps_per_pass) * B
+        n = min(B, n_local - a)
+        sc.bind_raw(slot_ptrs[j], n, shp[:n], sf[:n], ids_all[a:a + n])
         sc.score_bound()
-        dst = (i * B) % max(n_local - B + 1, 1)
-        pool_scores[dst:dst + B].copy_(sc.t["image_scores"][:B], non_blocking=True)
+        pool_scores[a:a + n].copy_(sc.t["image_scores"][:n], non_blocking=True)
+        return n
 
     def finish():
-        allsc = gather_scores(pool_scores[:n_local], pool_size, rank, world) if world > 1 else pool_scores
+        allsc = gather_scores(pool_scores, pool_size, rank, world) if world > 1 else pool_scores
         k = max(1, min(int(0.025 * pool_size), allsc.numel()))
         return pool_topk(allsc, k)
 
@@ -269,6 +329,11 @@ def main():
         step(i)
     finish()
     torch.cuda.synchronize()
+    # pairs and objects per image of a full batch (for the K2 / K3 work figures below)
+    S_ = spec.num_levels
+    nb0 = min(B, n_local)
+    pairs_per_image = float(sc.t["pair_off"][:nb0, S_].float().mean().item())
+    objs_per_image = float(sc.t["n_obj"][:nb0].float().mean().item())
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
@@ -278,8 +343,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    n_scored = 0
     for i in range(args.steps):
-        step(args.warmup + i)
+        n_scored += step(i)
     selected = finish()
     e1.record()
     torch.cuda.synchronize()
@@ -296,16 +362,24 @@ def main():
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * args.steps * B / (ms * 1e-3)
+    if world > 1:
+        t = torch.tensor([float(n_scored)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_scored = float(t.item())
+    else:
+        total_scored = float(n_scored)
+    value = total_scored / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (K1a), timed live above
     peak, peak_src = measured_peaks()
     names = ["k1a_keys", "k1b_select", "k1c_gather", "k3a_nms", "k3b_pairs", "k2_dirichlet", "k3c_hua"]
     stage_avg = {n: stage_ms[i] / max(calls.value, 1) for i, n in enumerate(names)}
-    k1a_bytes = B * (4 * spec.num_priors * spec.c_out + 4 * spec.num_priors)       # logits read + keys written
+    stage_tot_s = {n: stage_ms[i] * 1e-3 for i, n in enumerate(names)}                  # over the n_scored images
+    img_per_launch = n_scored / max(calls.value, 1)
+    k1a_bytes = img_per_launch * (4 * spec.num_priors * spec.c_out + 4 * spec.num_priors)   # logits read + keys written
     k1a_s = stage_avg["k1a_keys"] * 1e-3
     achieved = k1a_bytes / k1a_s / 1e9 if k1a_s > 0 else 0.0
-    k1_all_s = (stage_avg["k1a_keys"] + stage_avg["k1b_select"] + stage_avg["k1c_gather"]) * 1e-3
+    k1_all_s = stage_tot_s["k1a_keys"] + stage_tot_s["k1b_select"] + stage_tot_s["k1c_gather"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1a_traffic.json")
     if os.path.isfile(tpath):
@@ -314,15 +388,25 @@ def main():
     roofline = dict(bound="hbm", kernel="k1a_keys_kernel", achieved=achieved, peak=peak, unit="GB/s",
                     frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=k1a_bytes,
-                    k1_stage_achieved=B * spec.k1_bytes_per_image() / k1_all_s / 1e9 if k1_all_s > 0 else 0.0,
+                    k1_stage_achieved=n_scored * spec.k1_bytes_per_image() / k1_all_s / 1e9 if k1_all_s > 0 else 0.0,
                     stage_ms_per_step=stage_avg)
+    roofline["k1_stage_frac"] = roofline["k1_stage_achieved"] / peak
+    # ---- the sampling stage: compute-bound (draws/s + pipe utilisation, no byte roofline)
+    draws = n_scored * pairs_per_image * params.n_samples * spec.c_out
+    k2 = dict(bound="issue slots / XU pipe", draws_per_s=draws / stage_tot_s["k2_dirichlet"] if stage_tot_s["k2_dirichlet"] > 0 else 0.0,
+              share_of_step=stage_tot_s["k2_dirichlet"] / max(sum(stage_tot_s.values()), 1e-12),
+              draws_per_image=pairs_per_image * params.n_samples * spec.c_out)
+    ppath = os.path.join(ROOT, "profiles", "k2_pipes.json")
+    if os.path.isfile(ppath):
+        with open(ppath) as f:
+            k2.update(json.load(f))       # instr_per_draw, issue_active, pipe_xu, pipe_alu, pipe_fma from the last ncu capture
+    roofline["k2"] = k2
 
     # ---- aggregation-stage kernels against the same HBM peak (tiny algorithmic traffic,
     #      expected latency-bound - reported, not a target)
-    S_ = spec.num_levels
-    p_tot = float(sc.t["pair_off"][:B, S_].float().sum().item())
-    n_obj_tot = float(sc.t["n_obj"][:B].float().sum().item())
-    k3_bytes = 16.0 * (B * spec.k_tot + n_obj_tot) + 12.0 * p_tot + 4.0 * B
+    p_tot = pairs_per_image * img_per_launch
+    n_obj_tot = objs_per_image * img_per_launch
+    k3_bytes = 16.0 * (img_per_launch * spec.k_tot + n_obj_tot) + 12.0 * p_tot + 4.0 * img_per_launch
     k3_s = (stage_avg["k3b_pairs"] + stage_avg["k3c_hua"]) * 1e-3
     t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pool_all = torch.rand(pool_size, device=device)
@@ -337,12 +421,11 @@ def main():
     k4_bytes = 4.0 * pool_size + 8.0 * kk
     roofline["aggregation"] = dict(
         k3_pairs_hua=dict(bytes_per_step=k3_bytes, ms=k3_s * 1e3, achieved=k3_bytes / k3_s / 1e9 if k3_s > 0 else 0.0,
-                          frac=(k3_bytes / k3_s / 1e9 / peak) if k3_s > 0 else 0.0, pairs_per_image=p_tot / B,
+                          frac=(k3_bytes / k3_s / 1e9 / peak) if k3_s > 0 else 0.0, pairs_per_image=pairs_per_image,
                           note="latency-bound: one block per image"),
         k4_pool_topk=dict(bytes_per_launch=k4_bytes, ms=k4_s * 1e3, achieved=k4_bytes / k4_s / 1e9,
                           frac=k4_bytes / k4_s / 1e9 / peak, pool=pool_size, k=kk, note="single block, once per pool"),
-        k2_draws_per_s=(p_tot * params.n_samples * spec.c_out) / (stage_avg["k2_dirichlet"] * 1e-3)
-        if stage_avg["k2_dirichlet"] > 0 else 0.0)
+        k2_draws_per_s=k2["draws_per_s"])
 
     # ---- e2e: host buffers through mehhua_score_batch_host (pinned inputs, H2D + D2H timed)
     e2e = None
@@ -395,10 +478,12 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate, dt = cpu_reference_rate(spec, params, args.cpu_images, 2, cores)
-        cpu_baseline = dict(value=rate, unit=UNIT, cores=cores, kind="port",
+        rate, dt, kind = cpu_reference_rate(spec, params, args.cpu_images, 2, cores)
+        cpu_baseline = dict(value=rate, unit=UNIT, cores=cores, kind=kind,
                             sample=f"{args.cpu_images} images of {spec.name}, batch 2, T={params.n_samples}, "
-                                   f"oracle port on torch CPU, {dt:.1f} s")
+                                   f"{'AST-loaded reference functions' if kind == 'reference' else 'oracle port'} on torch CPU, {dt:.1f} s")
+        if not args.no_baseline_of_record:
+            cpu_baseline["baseline_of_record"] = baseline_of_record(params)
         if args.eager_gpu_images > 0:
             try:
                 r2, dt2 = eager_gpu_rate(spec, params, args.eager_gpu_images, 2, device)
@@ -413,7 +498,9 @@ def main():
                 config=dict(workload=spec.name, batch_per_gpu=B, ring_images_per_gpu=ring, samples=params.n_samples,
                             pool_size=pool_size, l2_policy=f"inputs larger than L2: {B * img_bytes / 1e6:.0f} MB per step, "
                             f"{ring * img_bytes / 1e9:.2f} GB ring", parallelism=f"pool sharded by image x{world}",
-                            selected=int(selected.numel()), status_bits=status),
+                            selected=int(selected.numel()), status_bits=status,
+                            pool_pass="whole shard scored once" if whole_shard else f"first {args.steps} of {steps_per_pass} steps",
+                            pool_coverage=min(1.0, total_scored / pool_size)),
                 roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=launches, clocks=clocks)
     print(json.dumps(line), flush=True)
     if world > 1:

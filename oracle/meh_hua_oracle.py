@@ -261,9 +261,12 @@ def compute_obj_unc(cls_scores: List[torch.Tensor], pos_bboxes: List[torch.Tenso
                     lvl_scores: List[torch.Tensor], lvl_L: List[torch.Tensor], *, head: int,
                     c_out: int, T: int = 500, fg_thr: float = 0.3, lambda_scale: float = 25.0,
                     lambda_eps: float = 1e-7, use_lambda: bool = True,
-                    sampler: SampleFn = default_sampler):
+                    sampler: SampleFn = default_sampler, analytic: bool = False,
+                    record_flat: Optional[bool] = None):
     """Returns (nested, flat): nested[i][obj][s][str(cls)] = (ale, epi) exactly as the reference
-    builds it, and a flat per-(image, level) record list for stage-wise comparison."""
+    builds it, and a flat per-(image, level) record list for stage-wise comparison.
+    analytic=True replaces the T drawn samples by their T -> infinity limits (dirichlet_expectations):
+    a deterministic stand-in for the Monte-Carlo step, used by the pool-level set-identity tests."""
     S = len(cls_scores)
     B = cls_scores[0].shape[0]
     n_obj = [p.size(1) for p in pos_bboxes]
@@ -294,18 +297,26 @@ def compute_obj_unc(cls_scores: List[torch.Tensor], pos_bboxes: List[torch.Tenso
             lam = lvl_L[s][i][pidx]
             lam_p = lam.mean() / (lam + lambda_eps) * lambda_scale
             alpha = ps * lam_p[:, None] if use_lambda else ps
-            smp = sampler(alpha, T, i, s)
-            total, ale, epi = uncertainty_from_samples(smp)
+            if analytic:
+                h_, e_, _ = dirichlet_expectations(alpha.double().cpu().numpy())
+                total = torch.from_numpy(h_.astype(np.float32)).to(alpha.device)
+                ale = torch.from_numpy(e_.astype(np.float32)).to(alpha.device)
+                epi = total - ale
+            else:
+                smp = sampler(alpha, T, i, s)
+                total, ale, epi = uncertainty_from_samples(smp)
             pcls = ps.argmax(dim=1)
             for obj in oidx.unique():
                 om = oidx == obj
                 for c in ps[om].argmax(dim=1).unique():
                     m = om & (pcls == c)
                     nested[i][obj][s][f"{c}"] = (ale[m].mean(), epi[m].mean())
-            if not ps.is_cuda:       # stage records for the parity tests (skipped by the eager-GPU baseline)
-                flat.append(dict(image=i, level=s, row=(pidx + start).numpy(), obj=oidx.numpy(),
-                                 cls=pcls.numpy(), lam_p=lam_p.numpy(), alpha=alpha.numpy(),
-                                 total=total.numpy(), ale=ale.numpy(), epi=epi.numpy()))
+            # stage records for the parity tests (skipped by the eager-GPU baseline unless asked for)
+            if record_flat or (record_flat is None and not ps.is_cuda):
+                n_ = lambda t_: t_.detach().cpu().numpy()
+                flat.append(dict(image=i, level=s, row=n_(pidx + start), obj=n_(oidx),
+                                 cls=n_(pcls), lam_p=n_(lam_p), alpha=n_(alpha),
+                                 total=n_(total), ale=n_(ale), epi=n_(epi)))
         start = end
     return nested, flat, level_fg
 
@@ -418,7 +429,8 @@ def score_batch(batch: Dict[str, object], *, head: int, c_out: int, stds, nms_pr
                 lambda_scale: float = 25.0, lambda_eps: float = 1e-7, use_lambda: bool = True,
                 agg: str = "objectSum_scaleMax_classSum", cls_w: bool = False,
                 sampler: SampleFn = default_sampler, rescale: bool = True,
-                topk_override: Optional[List[torch.Tensor]] = None) -> Dict[str, object]:
+                topk_override: Optional[List[torch.Tensor]] = None, analytic: bool = False,
+                record_flat: Optional[bool] = None) -> Dict[str, object]:
     pre = pre_stage(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
                     batch["img_shapes"], batch["scale_factors"], head=head, c_out=c_out, stds=stds,
                     nms_pre=nms_pre, score_thr=score_thr, nms_iou=nms_iou, max_per_img=max_per_img,
@@ -426,7 +438,7 @@ def score_batch(batch: Dict[str, object], *, head: int, c_out: int, stds, nms_pr
     nested, flat, level_fg = compute_obj_unc(
         batch["cls_scores"], pre["pos_bboxes"], pre["lvl_scores"], pre["lvl_L"], head=head,
         c_out=c_out, T=T, fg_thr=fg_thr, lambda_scale=lambda_scale, lambda_eps=lambda_eps,
-        use_lambda=use_lambda, sampler=sampler)
+        use_lambda=use_lambda, sampler=sampler, analytic=analytic, record_flat=record_flat)
     unc = aggregate_obj_scale_unc(nested, agg, cls_w)
     pre.update(nested=nested, flat=flat, level_fg=level_fg, image_scores=unc)
     return pre
