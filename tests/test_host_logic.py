@@ -183,18 +183,20 @@ def test_oracle_max_conf_matches_reference():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU oracle port of the reference path) needs no GPU and prints
-    one JSON line with the keys the driver reads."""
+    """`bench.py --impl reference` (the reference's CPU path: its own AST-loaded functions where
+    /root/reference is mounted, else the oracle port) needs no GPU and prints one JSON line with the
+    keys the driver reads."""
     import json
+    from oracle import ref_loader as RL
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload",
-                          "tiny_retina_coco", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
-                         timeout=600, cwd=ROOT)
+                          "tiny_retina_coco", "--steps", "2", "--warmup", "1", "--no-baseline-of-record"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 2 and line["gpu_launches"] == 0
     assert line["config"]["workload"] == "tiny_retina_coco"
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == ("reference" if RL.available() else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
