@@ -17,7 +17,7 @@ MAX_NMS_PRE = 4096
 ABI_VERSION = 4
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
-ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA = 1, 2, 4
+ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA, ST_CAPTURE_FALLBACK = 1, 2, 4, 8
 MODE_NMS, MODE_ALL = 0, 1
 
 
@@ -77,6 +77,7 @@ SYMBOLS = {
     "mehhua_stage_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mehhua_pool_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "mehhua_k4_pool_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "mehhua_debug_capture_counts": (C.c_int, [_CFG, _LV, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "mehhua_debug_philox": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mehhua_host_ctx_create": (C.c_int, [_CFG, _LV, C.c_int32, C.POINTER(_P)]),
     "mehhua_host_ctx_destroy": (None, [_P]),

@@ -8,6 +8,17 @@
 namespace mehhua {
 
 constexpr int kMaxLevels = MEHHUA_MAX_LEVELS;
+// Capture mode of K1 (sparse top-k levels, N >= kCapMinRatio * k): a pre-pass over 1/kCapStride of the level's
+// warps estimates the key of rank kCapTargetNum / kCapTargetDen * k; the streaming pass parks the score row of every prior at or above
+// it (at most kCapRows per (image, level)); the select then runs over the parked rows only.  A level
+// whose estimate misses (fewer than k or more than kCapRows parked rows) falls back to the select
+// over all keys and the strided gather - results are identical either way.
+constexpr int kCapRows = 4096;
+constexpr int kCapPad = 4;            // floats after the C exponentials of a parked row: 1/sum, score normaliser, 2 unused
+constexpr int kCapStride = 32;
+constexpr int kCapTargetNum = 7, kCapTargetDen = 4;
+constexpr int kCapMinRatio = 16;
+constexpr int kCapSampleMax = 8192;   // sampled priors per (image, level) the threshold kernel can hold
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -27,7 +38,7 @@ struct LevelDev {
   int topk;   // 1 when n > k (the per-level top-k is active)
   int rescan; // 1 when the level's rows are produced by the coalesced rescan kernel (no top-k, or k >= n/8)
   int rtile0; // first rescan tile of the level inside one image's rescan tile list
-  int pad;
+  int cap;    // >= 0: the level's rows are CAPTURED while K1a streams it (index of the level among the capture levels); -1: not
 };
 
 // Everything a kernel needs about the batch, passed by value (__grid_constant__).
@@ -39,6 +50,7 @@ struct Plan {
   int row_stride;       // rows per image in score_rows / lam_rows (K; pair_cap in Entropy_ALL mode)
   int tiles_per_image;  // K1a tiles per image
   int rtiles_per_image; // K1c rescan tiles per image
+  int n_cap_levels;     // levels in capture mode
   int nms_pre, max_per_img, pair_cap, n_samples;
   int use_lambda, agg_object, agg_scale, agg_class, cls_w, rescale;
   float score_thr, nms_iou, fg_thr, obj_thr, cluster_iou, lambda_scale, lambda_eps;
@@ -61,6 +73,11 @@ struct Workspace {
   unsigned* fg_list;           // [B, pair_cap] Entropy_ALL: (level << 28 | prior) of every foreground prior
   int* fg_cnt;                 // [B]
   float* lam_part;             // [B, tiles_per_image] per-tile lambda sums (Entropy_ALL)
+  float* tau;                  // [B, S]   capture threshold of a capture level (K1t)
+  int* cap_cnt;                // [B, S]   rows captured so far / in total
+  unsigned long long* cap_comp;// [B, n_cap_levels, kCapRows] composite (key bits << 32 | ~position) of each captured row
+  float* cap_scores;           // [B, n_cap_levels, kCapRows, C + kCapPad] exponentials + normalisers of each captured row
+  int* row_slot;               // [B, K]   capture slot of a kept row, -1 = take it from the logits (gather)
   size_t bytes;
 };
 
@@ -138,6 +155,26 @@ __device__ __forceinline__ void block_bitonic_desc(unsigned long long* buf, int 
         const bool desc = (lo & size) == 0;
         const unsigned long long a = buf[lo], b = buf[hi];
         if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Same, carrying a 16-bit payload with every key.
+template <int THREADS>
+__device__ __forceinline__ void block_bitonic_desc_kv(unsigned long long* buf, unsigned short* val, int n2) {
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = buf[lo], b = buf[hi];
+        if ((a < b) == desc) {
+          buf[lo] = b; buf[hi] = a;
+          const unsigned short t = val[lo]; val[lo] = val[hi]; val[hi] = t;
+        }
       }
       __syncthreads();
     }

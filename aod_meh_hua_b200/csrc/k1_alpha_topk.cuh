@@ -1,5 +1,12 @@
 // K1: logits -> softmax / score -> ranking key (K1a, the HBM-streaming kernel) -> per-level top-k
-// (K1b, block radix select) -> gather of the kept rows, lambda, decoded boxes, NMS candidates (K1c).
+// (K1b, block radix select) -> the kept rows, lambda, decoded boxes, NMS candidates (K1c).
+// Where do the kept rows' scores come from?  Three forms, chosen per level by the plan:
+//   capture : sparse top-k levels (k << N).  K1t reads 1/32 of the level's warps and estimates the key of
+//             rank 2k; K1a parks the score row of every prior at or above it while the logits are in
+//             registers; K1b sorts the parked rows only; K1c reads 320-byte parked rows instead of
+//             re-reading C strided sectors per row.  A level whose estimate misses falls back to gather.
+//   gather  : the row's C logits re-read with stride H*W (one 32-byte sector per logit).
+//   rescan  : dense levels (k >= N/8 or no top-k): a second coalesced pass.
 //
 // Reference semantics: _get_bboxes per-level block (mmdet/models/dense_heads/Lambda_L2.py:264-326,
 // My_L_ssd_head.py:325-361), delta2bbox (core/bbox/coder/delta_xywh_bbox_coder.py:205-267), the
@@ -13,7 +20,7 @@ namespace mehhua {
 constexpr int kK1aThreads = 128;   // one prior position per thread, C logits in registers
 constexpr int kSelThreads = 1024;
 constexpr int kSelCap = 4096;      // >= MEHHUA_MAX_NMS_PRE
-constexpr size_t kSelSmem = kSelCap * 8 + 4096 * 4 + 40 * 4;
+constexpr size_t kSelSmem = kSelCap * 8 + 4096 * 4 + 40 * 4 + kSelCap * 2;
 constexpr int kGatherThreads = 128;
 
 // Softmax of one prior held in registers.  On return x[c] = exp(logit_c - max) (unnormalised),
@@ -90,10 +97,34 @@ __device__ __forceinline__ void level_maxconf_update(unsigned* dst, float inv) {
 // load instruction is one coalesced 128-byte line of one class plane.
 // C == 0 selects the generic (runtime class count) path.
 // ------------------------------------------------------------------------------------------
+// The ranking composite of prior position j (= a*HW + hw) with key `key`: exact key ties go to the lower
+// position.  Keys outside [0, 2) (negatives, NaN) are clamped so that composites stay below 2^62.
+__device__ __forceinline__ unsigned long long k1_composite(const float key, const int j) {
+  unsigned kb = __float_as_uint(key);
+  if (kb > 0x3fffffffu) kb = (kb & 0x80000000u) ? 0u : 0x3fffffffu;   // negatives / >= 2.0 / NaN
+  return ((unsigned long long)kb << 32) | (unsigned long long)(0xffffffffu - (unsigned)j);
+}
+
+// key of one prior from its logits; on return x[c] = score_c (C > 0)
+template <int C, int HEAD>
+__device__ __forceinline__ float k1_key(float (&x)[C > 0 ? C : 1], const float* __restrict__ src, const size_t stride,
+                                        const int CC, float& inv, float& pfg, float& den) {
+  if constexpr (C > 0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) x[c] = __ldg(src + (size_t)c * stride);
+    softmax_regs<C, HEAD>(x, inv, den, pfg);
+  } else {
+    float m;
+    softmax_stream<HEAD>(src, stride, CC, m, inv, den, pfg);
+  }
+  return (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pfg, den) : pfg;
+}
+
 template <int C, int HEAD>
 __global__ void __launch_bounds__(kK1aThreads)
 k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* __restrict__ level_fg,
-                unsigned* __restrict__ level_maxconf) {
+                unsigned* __restrict__ level_maxconf, const float* __restrict__ tau, int* __restrict__ cap_cnt,
+                unsigned long long* __restrict__ cap_comp, float* __restrict__ cap_scores) {
   const int t = blockIdx.x;
   const int b = t / p.tiles_per_image;
   const int ti = t - b * p.tiles_per_image;
@@ -105,23 +136,106 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
   const int lt = ti - L.tile0;
   const int a = lt / L.tpp;
   const int hw = (lt - a * L.tpp) * kK1aThreads + threadIdx.x;
-  if (hw >= L.HW) return;
+  const bool live = hw < L.HW;        // lanes past the end of the plane stay for the warp-wide capture step
   const int CC = (C > 0) ? C : p.C;
-  const float* __restrict__ src = L.logits + ((size_t)(b * L.A + a) * CC) * L.HW + hw;
-  float inv, den, pfg;
-  if constexpr (C > 0) {
-    float x[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) x[c] = __ldg(src + (size_t)c * L.HW);
-    softmax_regs<C, HEAD>(x, inv, den, pfg);
-  } else {
-    float m;
-    softmax_stream<HEAD>(src, (size_t)L.HW, CC, m, inv, den, pfg);
+  float x[C > 0 ? C : 1];
+  float inv = 0.f, den = 0.f, pfg = 0.f, key = 0.f;
+  if (live) {
+    const float* __restrict__ src = L.logits + ((size_t)(b * L.A + a) * CC) * L.HW + hw;
+    key = k1_key<C, HEAD>(x, src, (size_t)L.HW, CC, inv, pfg, den);
+    keys[(size_t)b * p.N + L.n_off + a * L.HW + hw] = key;
+    if (pfg > p.fg_thr) level_fg[b * p.S + s] = 1;
+    if (level_maxconf) level_maxconf_update(level_maxconf + b * p.S + s, inv);
   }
-  const float key = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pfg, den) : pfg;
-  keys[(size_t)b * p.N + L.n_off + a * L.HW + hw] = key;
-  if (pfg > p.fg_thr) level_fg[b * p.S + s] = 1;
-  if (level_maxconf) level_maxconf_update(level_maxconf + b * p.S + s, inv);
+  if constexpr (C > 0) {
+    // capture: park the row of every prior at or above the level's threshold (about 1.75 k of them per
+    // (image, level)): its C exponentials as they sit in registers (128-bit stores, one contiguous
+    // 4*C-byte row per lane) and the two normalisers; K1c turns them into scores with the same two
+    // multiplications it applies to a gathered row.
+    if (L.cap < 0 || tau == nullptr) return;             // block-uniform
+    const unsigned full = 0xffffffffu;
+    __syncwarp(full);                                     // reconverge after the divergent updates above
+    const bool park = live && key >= __ldg(tau + b * p.S + s);
+    const unsigned pm = __ballot_sync(full, park);
+    if (pm != 0u) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cap_cnt + b * p.S + s, __popc(pm));
+      base = __shfl_sync(full, base, 0);
+      const int slot = base + __popc(pm & ((1u << lane) - 1u));
+      if (park && slot < kCapRows) {
+        const size_t e = ((size_t)b * p.n_cap_levels + L.cap) * kCapRows + slot;
+        cap_comp[e] = k1_composite(key, a * L.HW + hw);
+        float* dst = cap_scores + e * (C + kCapPad);
+        if constexpr (C % 4 == 0) {
+#pragma unroll
+          for (int c = 0; c < C; c += 4) __stcs(reinterpret_cast<float4*>(dst + c), make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]));
+          __stcs(reinterpret_cast<float4*>(dst + C), make_float4(inv, den, 0.f, 0.f));
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) __stcs(dst + c, x[c]);
+          __stcs(dst + C, inv);
+          __stcs(dst + C + 1, den);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1t: capture threshold of every capture level of every image.  grid = (S, B), one block reads the
+// logits of 1/stride of the level's warps (whole 128-byte lines per class, as K1a does), computes their
+// keys and takes the key of rank ~ kCapTarget * k * (sampled / N) among them.
+// ------------------------------------------------------------------------------------------
+constexpr int kThrThreads = 512;     // C logits live in registers: 128 registers per thread
+constexpr size_t kThrSmem = (size_t)kCapSampleMax * 4 + (size_t)kSelCap * 8 + 4096 * 4 + 40 * 4;
+
+template <int C, int HEAD>
+__global__ void __launch_bounds__(kThrThreads)
+k1t_threshold_kernel(const __grid_constant__ Plan p, float* __restrict__ tau, unsigned* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char k1t_smem[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(k1t_smem);   // kSelCap
+  float* skeys = reinterpret_cast<float*>(buf + kSelCap);                       // kCapSampleMax
+  int* hist = reinterpret_cast<int*>(skeys + kCapSampleMax);                    // 4096
+  int* sh = hist + 4096;                                                        // 40
+  const int s = blockIdx.x, b = blockIdx.y;
+  const LevelDev& L = p.lv[s];
+  if (L.cap < 0) return;
+  const int CC = (C > 0) ? C : p.C;
+  const int wpp = (L.HW + 31) >> 5;                       // warps per (image, anchor) plane
+  const int total = wpp * L.A;
+  int stride = kCapStride;
+  while ((total + stride - 1) / stride > kCapSampleMax / 32) stride <<= 1;
+  const int phase = (b * 7 + s * 3) % stride;
+  const int nsw = total > phase ? (total - phase + stride - 1) / stride : 0;   // sampled warps
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x >> 5; i < nsw; i += kThrThreads / 32) {
+    const int g = phase + i * stride;
+    const int a = g / wpp, hw = ((g - a * wpp) << 5) + lane;
+    float key = -1.f;                                     // not an element
+    if (hw < L.HW) {
+      float x[C > 0 ? C : 1];
+      float inv, den, pfg;
+      key = k1_key<C, HEAD>(x, L.logits + ((size_t)(b * L.A + a) * CC) * L.HW + hw, (size_t)L.HW, CC, inv, pfg, den);
+    }
+    skeys[i * 32 + lane] = key;
+  }
+  __syncthreads();
+  const int n = nsw * 32;
+  int valid = 0;     // sampled priors: every sampled warp is full except the last one of a plane
+  for (int i = threadIdx.x; i < n; i += kThrThreads) valid += skeys[i] >= 0.f ? 1 : 0;
+  valid = block_incl_scan<kThrThreads>(valid, sh);
+  if (threadIdx.x == kThrThreads - 1) sh[39] = valid;
+  __syncthreads();
+  valid = sh[39];
+  __syncthreads();
+  const int r = (int)(((long long)kCapTargetNum * L.k * valid + (long long)kCapTargetDen * L.n - 1) / ((long long)kCapTargetDen * L.n)) + 1;
+  auto get = [&](int j) -> unsigned long long { return skeys[j] >= 0.f ? k1_composite(skeys[j], j) : 0ull; };
+  const int cnt = block_collect_topk<kThrThreads, kSelCap, 0>(get, n, min(r, kSelCap), ~0ull, buf, hist, sh, status);
+  if (threadIdx.x == 0) {
+    // fewer sampled priors than the rank asked for: park everything (the level then falls back if that is too many)
+    tau[b * p.S + s] = (cnt >= r) ? __uint_as_float((unsigned)(buf[r - 1] >> 32)) : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -130,25 +244,49 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSelThreads)
 k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys,
-                  int* __restrict__ topk_idx, int* __restrict__ inv_map, unsigned* __restrict__ status) {
+                  int* __restrict__ topk_idx, int* __restrict__ inv_map, const int* __restrict__ cap_cnt,
+                  const unsigned long long* __restrict__ cap_comp, int* __restrict__ row_slot,
+                  unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k1b_smem[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(k1b_smem);   // kSelCap
   int* hist = reinterpret_cast<int*>(buf + kSelCap);                            // 4096
   int* sh = hist + 4096;                                                        // 40
+  unsigned short* slot = reinterpret_cast<unsigned short*>(sh + 40);            // kSelCap
   const int s = blockIdx.x, b = blockIdx.y;
   const LevelDev& L = p.lv[s];
   if (!L.topk) return;
+  int* out = topk_idx + (size_t)b * p.K + L.k_off;
+  if (L.cap >= 0) {
+    // capture level: the k best are among the parked rows when at least k were parked and none was dropped
+    const int nc = cap_cnt[b * p.S + s];
+    int* rs = row_slot + (size_t)b * p.K + L.k_off;
+    if (nc >= L.k && nc <= kCapRows) {
+      const unsigned long long* cc = cap_comp + ((size_t)b * p.n_cap_levels + L.cap) * kCapRows;
+      int n2 = 1;
+      while (n2 < nc) n2 <<= 1;
+      for (int i = threadIdx.x; i < n2; i += kSelThreads) {
+        buf[i] = i < nc ? cc[i] : 0ull;
+        slot[i] = (unsigned short)i;
+      }
+      __syncthreads();
+      block_bitonic_desc_kv<kSelThreads>(buf, slot, n2);
+      for (int i = threadIdx.x; i < L.k; i += kSelThreads) {
+        const int j = (int)(0xffffffffu - (unsigned)(buf[i] & 0xffffffffull));
+        const int a = j / L.HW;
+        out[i] = (j - a * L.HW) * L.A + a;
+        rs[i] = (int)slot[i];
+      }
+      return;
+    }
+    for (int i = threadIdx.x; i < L.k; i += kSelThreads) rs[i] = -1;      // fall back: select over all keys, rows by gather
+    if (threadIdx.x == 0) atomicOr(status, MEHHUA_ST_CAPTURE_FALLBACK);
+  }
   const float* kp = keys + (size_t)b * p.N + L.n_off;
   // composite = key bits << 32 | ~position, position j = a*HW + hw (the key array is anchor-major):
   // exact key ties go to the lower position.  The prior index n = hw*A + a is only rebuilt for
   // the k winners.
-  auto get = [&](int j) -> unsigned long long {
-    unsigned kb = __float_as_uint(__ldcg(kp + j));
-    if (kb > 0x3fffffffu) kb = (kb & 0x80000000u) ? 0u : 0x3fffffffu;   // negatives / >= 2.0 / NaN
-    return ((unsigned long long)kb << 32) | (unsigned long long)(0xffffffffu - (unsigned)j);
-  };
+  auto get = [&](int j) -> unsigned long long { return k1_composite(__ldcg(kp + j), j); };
   const int cnt = block_collect_topk<kSelThreads, kSelCap, 0>(get, L.n, L.k, ~0ull, buf, hist, sh, status);
-  int* out = topk_idx + (size_t)b * p.K + L.k_off;
   const int k = min(L.k, cnt);
   int* inv = inv_map + (size_t)b * p.N + L.n_off;
   if (L.rescan) {       // dense level: the rescan kernel finds rows through the inverse map
@@ -188,7 +326,8 @@ __device__ __forceinline__ void k1_row_body(const Plan& p, const LevelDev& L, co
                                             float* __restrict__ score_rows, float* __restrict__ lam_rows,
                                             float* __restrict__ boxes, float* __restrict__ row_max,
                                             int* __restrict__ row_argmax, float (&x)[C > 0 ? C : 1],
-                                            float* tile_row, int& ncand, float& bmax, float*& srow) {
+                                            float* tile_row, int& ncand, float& bmax, float*& srow,
+                                            const bool scores_ready = false) {
   const int CC = (C > 0) ? C : p.C;
   const int NF = p.num_fg;
   float4 box;
@@ -197,13 +336,16 @@ __device__ __forceinline__ void k1_row_body(const Plan& p, const LevelDev& L, co
     srow = score_rows + ((size_t)b * p.K + r) * CC;
     float best = -1.f;
     int arg = 0;
-    if constexpr (C > 0) {      // x[] holds the row's logits, loaded by the caller
-      float inv, den, pfg;
-      softmax_regs<C, HEAD>(x, inv, den, pfg);
+    if constexpr (C > 0) {      // x[] holds the row's logits (or, scores_ready, its parked scores), loaded by the caller
+      float inv = 1.f, den = 1.f, pfg;
+      if (!scores_ready) softmax_regs<C, HEAD>(x, inv, den, pfg);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float pc = __fmul_rn(x[c], inv);
-        const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
+        float sc = x[c];
+        if (!scores_ready) {
+          const float pc = __fmul_rn(x[c], inv);
+          sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
+        }
         x[c] = sc;
         if (sc > best) { best = sc; arg = c; }
         if (c < NF && sc > p.score_thr) ++ncand;
@@ -332,7 +474,8 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
                   float* __restrict__ score_rows, float* __restrict__ lam_rows,
                   float* __restrict__ boxes, float* __restrict__ row_max, int* __restrict__ row_argmax,
                   unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
-                  unsigned* __restrict__ cand_maxc) {
+                  unsigned* __restrict__ cand_maxc, const int* __restrict__ row_slot,
+                  const float* __restrict__ cap_scores) {
   const int b = blockIdx.y;
   const int r = blockIdx.x * kGatherThreads + threadIdx.x;
   int ncand = 0;
@@ -346,10 +489,37 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
       const int n = topk_idx[(size_t)b * p.K + r];
       const int hw = n / L.A;
       float x[C > 0 ? C : 1];
-      k1_load_logits<C>(L, b, n - hw * L.A, hw, x);
+      bool parked = false;
+      if constexpr (C > 0) {
+        const int slot = (L.cap >= 0) ? row_slot[(size_t)b * p.K + r] : -1;
+        if (slot >= 0) {        // capture level: the row was parked by K1a (one contiguous read): exponentials + normalisers
+          const float* src = cap_scores + (((size_t)b * p.n_cap_levels + L.cap) * kCapRows + slot) * (C + kCapPad);
+          float inv, den;
+          if constexpr (C % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < C; c += 4) {
+              const float4 v = __ldcs(reinterpret_cast<const float4*>(src + c));
+              x[c] = v.x; x[c + 1] = v.y; x[c + 2] = v.z; x[c + 3] = v.w;
+            }
+            const float4 nd = __ldcs(reinterpret_cast<const float4*>(src + C));
+            inv = nd.x; den = nd.y;
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c] = __ldcs(src + c);
+            inv = __ldcs(src + C); den = __ldcs(src + C + 1);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float pc = __fmul_rn(x[c], inv);
+            x[c] = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
+          }
+          parked = true;
+        }
+      }
+      if (!parked) k1_load_logits<C>(L, b, n - hw * L.A, hw, x);
       if (C == 0) tile_row = score_rows + ((size_t)b * p.K + r) * p.C;
       k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
-                           row_argmax, x, tile_row, ncand, bmax, srow);
+                           row_argmax, x, tile_row, ncand, bmax, srow, parked);
     }
   }
   if constexpr (C > 0) k1_flush_rows<C>(tile + (threadIdx.x & ~31) * K1Tile<C>::stride, srow);

@@ -65,6 +65,14 @@ void timer_mark(cudaStream_t st, int slot) {
   cudaEventRecord(g_timer.ev[g_timer.calls * (kStages + 1) + slot], st);
 }
 
+bool k1_has_typed(int head, int c_out) {      // the <C, HEAD> instantiations of launch_k1
+  return head == MEHHUA_HEAD_RETINA ? (c_out == 20 || c_out == 80) : (c_out == 21 || c_out == 81);
+}
+bool no_capture() {
+  static const bool v = [] { const char* e = getenv("MEHHUA_NO_CAPTURE"); return e && e[0] == '1'; }();
+  return v;
+}
+
 int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool need_ptrs, Plan* out) {
   if (!cfg || !lv) return arg_fail("null config / levels");
   if (cfg->num_levels < 1 || cfg->num_levels > kMaxLevels) return arg_fail("num_levels must be 1..8");
@@ -104,6 +112,12 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
     L.rescan = (!L.topk || (long long)MEHHUA_RESCAN_RATIO * L.k >= n) ? 1 : 0;
     L.rtile0 = (int)rtile0;
     if (L.rescan) rtile0 += (long long)L.tpp * L.A;
+    // sparse top-k levels of the class counts with a register-resident instantiation are captured
+    // while K1a streams them (k1_alpha_topk.cuh); MEHHUA_NO_CAPTURE=1 in the environment forces the gather form
+    L.cap = -1;
+    if (L.topk && !L.rescan && n >= (long long)kCapMinRatio * L.k && k1_has_typed(cfg->head, cfg->c_out) &&
+        cfg->mode == MEHHUA_MODE_NMS && !no_capture())
+      L.cap = p.n_cap_levels++;
     n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
   }
   if (n_off > (1ll << 30) || k_off > (1 << 20) || tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
@@ -144,6 +158,11 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   const size_t o_fgl = take((size_t)p.B * p.pair_cap * sizeof(unsigned));
   const size_t o_fgc = take((size_t)p.B * sizeof(int));
   const size_t o_lamp = take((size_t)p.B * p.tiles_per_image * sizeof(float));
+  const size_t o_tau = take((size_t)p.B * p.S * sizeof(float));
+  const size_t o_capc = take((size_t)p.B * p.S * sizeof(int));
+  const size_t o_slot = take((size_t)p.B * p.K * sizeof(int));
+  const size_t o_ccomp = take((size_t)p.B * p.n_cap_levels * kCapRows * sizeof(unsigned long long));
+  const size_t o_cscore = take((size_t)p.B * p.n_cap_levels * kCapRows * (p.C + kCapPad) * sizeof(float));
   if (ws) {
     char* b = static_cast<char*>(base);
     ws->keys = reinterpret_cast<float*>(b + o_keys);
@@ -158,6 +177,11 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
     ws->fg_list = reinterpret_cast<unsigned*>(b + o_fgl);
     ws->fg_cnt = reinterpret_cast<int*>(b + o_fgc);
     ws->lam_part = reinterpret_cast<float*>(b + o_lamp);
+    ws->tau = reinterpret_cast<float*>(b + o_tau);
+    ws->cap_cnt = reinterpret_cast<int*>(b + o_capc);
+    ws->row_slot = reinterpret_cast<int*>(b + o_slot);
+    ws->cap_comp = reinterpret_cast<unsigned long long*>(b + o_ccomp);
+    ws->cap_scores = reinterpret_cast<float*>(b + o_cscore);
     ws->bytes = off;
   }
   return off;
@@ -235,15 +259,23 @@ template <int C, int HEAD>
 int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes, const float* scale_factors,
                     const mehhua_buffers_t* o, cudaStream_t st) {
   timer_mark(st, 0);
+  if (p.n_cap_levels > 0) {      // capture thresholds from a 1/32 sample of the sparse top-k levels
+    CU(cudaMemsetAsync(ws.cap_cnt, 0, (size_t)p.B * p.S * sizeof(int), st));
+    if (int rc = ensure_dyn_smem(k1t_threshold_kernel<C, HEAD>, kThrSmem)) return rc;
+    k1t_threshold_kernel<C, HEAD><<<dim3(p.S, p.B), kThrThreads, kThrSmem, st>>>(p, ws.tau, ws.status);
+    LAUNCHED("k1t_threshold_kernel");
+  }
   k1a_keys_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
-      p, ws.keys, o->level_fg, reinterpret_cast<unsigned*>(o->level_maxconf));
+      p, ws.keys, o->level_fg, reinterpret_cast<unsigned*>(o->level_maxconf),
+      p.n_cap_levels > 0 ? ws.tau : nullptr, ws.cap_cnt, ws.cap_comp, ws.cap_scores);
   LAUNCHED("k1a_keys_kernel");
   timer_mark(st, 1);
   bool any_topk = false;
   for (int s = 0; s < p.S; ++s) any_topk |= p.lv[s].topk != 0;
   if (any_topk) {
     if (int rc = ensure_dyn_smem(k1b_select_kernel, kSelSmem)) return rc;
-    k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.inv_map, ws.status);
+    k1b_select_kernel<<<dim3(p.S, p.B), kSelThreads, kSelSmem, st>>>(p, ws.keys, o->topk_idx, ws.inv_map, ws.cap_cnt,
+                                                                     ws.cap_comp, ws.row_slot, ws.status);
     LAUNCHED("k1b_select_kernel");
   }
   timer_mark(st, 2);
@@ -252,7 +284,7 @@ int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes,
   if (any_gather) {
     k1c_gather_kernel<C, HEAD><<<dim3((p.K + kGatherThreads - 1) / kGatherThreads, p.B), kGatherThreads, 0, st>>>(
         p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
-        o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
+        o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc, ws.row_slot, ws.cap_scores);
     LAUNCHED("k1c_gather_kernel");
   }
   if (p.rtiles_per_image > 0) {
@@ -578,6 +610,24 @@ int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int
                                                          reinterpret_cast<long long*>(idx_out), n_selected_out,
                                                          static_cast<unsigned*>(workspace));
   LAUNCHED("k4_pool_topk_kernel");
+  return 0;
+}
+
+// debug: rows parked per (image, level) by the last K1 call on this workspace, -1 for levels not in capture mode
+int mehhua_debug_capture_counts(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B, void* workspace,
+                                void* stream, int32_t* counts_out) {
+  if (!workspace || !counts_out) return arg_fail("null pointer");
+  Plan p;
+  int rc = build_plan(cfg, levels, B, false, &p);
+  if (rc) return rc;
+  Workspace ws;
+  carve(p, workspace, &ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU(cudaMemcpyAsync(counts_out, ws.cap_cnt, (size_t)B * p.S * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < p.S; ++s)
+      if (p.lv[s].cap < 0) counts_out[b * p.S + s] = -1;
   return 0;
 }
 

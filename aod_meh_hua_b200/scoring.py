@@ -263,6 +263,14 @@ class Scorer:
         self._call("mehhua_read_status", *self._common(), self.workspace.data_ptr(), self._stream(), C.byref(st))
         return int(st.value)
 
+    def capture_counts(self) -> np.ndarray:
+        """Rows parked per (image, level) by the last K1 call (capture mode of K1, csrc/k1_alpha_topk.cuh);
+        -1 for levels that are not in capture mode.  int32 [B, S]."""
+        out = np.zeros((self._B, self.spec.num_levels), dtype=np.int32)
+        self._call("mehhua_debug_capture_counts", *self._common(), self.workspace.data_ptr(), self._stream(),
+                   out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
     def check_status(self) -> int:
         """Raise on data-dependent failures; returns the informational bits."""
         st = self.read_status()

@@ -49,6 +49,7 @@ extern "C" {
 #define MEHHUA_ST_PAIR_OVERFLOW   1u  /* an image produced more (box, object) pairs than pair_cap */
 #define MEHHUA_ST_SELECT_SLOWPATH 2u  /* info: a top-k needed extra radix passes (ties / dense bins) */
 #define MEHHUA_ST_BAD_ALPHA       4u  /* info: a Dirichlet alpha <= 0 was met (treated as clamped) */
+#define MEHHUA_ST_CAPTURE_FALLBACK 8u /* info: a level's capture estimate missed; its rows came from the gather path */
 
 #define MEHHUA_HEAD_RETINA 0   /* Lambda_L2Net: C_out = C, score = p / (sum(p) + 1e-20 + 1e-9) */
 #define MEHHUA_HEAD_SSD    1   /* MyLSSDHead:   C_out = C + 1 (background last), score = p     */
@@ -225,6 +226,11 @@ size_t mehhua_pool_topk_workspace_bytes(int64_t n);
 int    mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k,
                            int64_t* idx_out, int32_t* n_selected_out, void* workspace,
                            size_t workspace_bytes, void* stream);
+
+/* Diagnostic: rows parked per (image, level) by the last K1 call on this workspace (capture mode of K1, see
+ * csrc/k1_alpha_topk.cuh), -1 for levels that are not in capture mode.  counts_out: host int32[B * num_levels]. */
+int mehhua_debug_capture_counts(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B, void* workspace,
+                                void* stream, int32_t* counts_out);
 
 /* Known-answer hook for the Philox4x32 block of K2 (tests): ctr[4], key[2] -> out[8], host arrays:
  * out[0..3] = the 10-round block, out[4..7] = the 7-round block (the one K2's sampler uses). */

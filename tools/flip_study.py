@@ -14,7 +14,9 @@ by its T -> infinity limit so that image scores are comparable.  Counted per dec
   level_fg     (image, level) foreground flags                                (Lambda_L2.py:496-502)
   nms_keep     detections (flat row*C+class) kept by one side only             (bbox_nms.py:41-93)
   n_obj        images whose object count differs                               (Lambda_L2.py:344)
-  pairs        (row prior, object) pairs of one side only                      (Lambda_L2.py:505-509)
+  obj_order    images whose objects (detections above 0.3) come in a different order (near-tied det scores)
+  pairs        (row prior, object) pairs of one side only, an object being identified by the detection
+               it is, not by its rank                                          (Lambda_L2.py:505-509)
   pair_cls     common pairs whose class key differs                            (Lambda_L2.py:526)
   score        images whose score differs by more than 1e-4 relative
   selected     ids in one side's top-2.5 % set but not the other's              (active_datasets.py:124)
@@ -34,7 +36,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-KEYS = ["topk_set", "topk_order", "level_fg", "nms_keep", "n_obj", "pairs", "pair_cls", "score"]
+KEYS = ["topk_set", "topk_order", "level_fg", "nms_keep", "n_obj", "obj_order", "pairs", "pair_cls", "score"]
 
 
 def compare(spec, res, out, B, counts, totals):
@@ -80,13 +82,22 @@ def compare(spec, res, out, B, counts, totals):
         rg = res.pair_row[b, :n].cpu().numpy()
         og = res.pair_obj[b, :n].cpu().numpy()
         cg = res.pair_cls[b, :n].cpu().numpy()
-        pg = {(int(lvl_of_row[r]), int(prior_got[b][r]), int(o)): int(c) for r, o, c in zip(rg, og, cg)}
+        # an object is identified by the detection it is (level, prior, class), not by its rank among the
+        # detections: two near-tied detection scores may swap ranks without changing any membership
+        def det_ids(flat, prior):
+            nfg = spec.num_classes
+            return [(int(lvl_of_row[f // nfg]), int(prior[f // nfg]), int(f % nfg)) for f in flat]
+        ids_g = det_ids(res.det_flat[b, :n_det[b]].cpu().numpy().astype(np.int64), prior_got[b])
+        ids_w = det_ids(dw.astype(np.int64), prior_want[b])
+        counts["obj_order"] += int(ids_g[:nobj_w] != ids_w[:nobj_w])
+        totals["obj_order"] += 1
+        pg = {(int(lvl_of_row[r]), int(prior_got[b][r]), ids_g[o]): int(c) for r, o, c in zip(rg, og, cg)}
         pw = {}
         for rec in out["flat"]:
             if rec["image"] != b:
                 continue
             for r, o, c in zip(rec["row"], rec["obj"], rec["cls"]):
-                pw[(int(lvl_of_row[r]), int(prior_want[b][r]), int(o))] = int(c)
+                pw[(int(lvl_of_row[r]), int(prior_want[b][r]), ids_w[o])] = int(c)
         counts["pairs"] += len(set(pg) ^ set(pw))
         totals["pairs"] += len(pw)
         common = set(pg) & set(pw)
@@ -118,6 +129,8 @@ def main():
              f"analytic (T -> infinity) uncertainty on every side",
              f"# torch {torch.__version__}, {torch.cuda.get_device_name(0)}"]
     for arm, cfg in arms.items():
+        if cfg["n"] <= 0:
+            continue
         counts = {k: 0 for k in KEYS}
         totals = {k: 0 for k in KEYS}
         got_all, want_all = [], []
