@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmehhua.so")
 MAX_LEVELS = 8
 MAX_DETS = 256
 MAX_NMS_PRE = 4096
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
 ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA, ST_CAPTURE_FALLBACK = 1, 2, 4, 8
@@ -40,12 +40,12 @@ class Config(C.Structure):
                 ("agg_scale", C.c_int32), ("agg_class", C.c_int32), ("cls_w", C.c_int32),
                 ("means", C.c_float * 4), ("stds", C.c_float * 4), ("wh_ratio_clip", C.c_float),
                 ("rescale", C.c_int32), ("pair_cap", C.c_int32), ("mode", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("activation", C.c_int32), ("seed", C.c_uint64)]
 
 
 BUFFER_FIELDS = ["score_rows", "lam_rows", "boxes", "topk_idx", "row_max", "row_argmax", "level_fg",
                  "dets", "det_labels", "det_flat", "n_det", "n_obj", "pair_row", "pair_obj",
-                 "pair_cls", "pair_off", "lam_mean", "pair_unc", "image_scores", "level_maxconf", "pair_avg"]
+                 "pair_cls", "pair_off", "lam_mean", "pair_unc", "image_scores", "level_maxconf", "group_unc", "pair_avg"]
 
 
 class Buffers(C.Structure):

@@ -53,6 +53,8 @@ struct Plan {
   int n_cap_levels;     // levels in capture mode
   int nms_pre, max_per_img, pair_cap, n_samples;
   int use_lambda, agg_object, agg_scale, agg_class, cls_w, rescale;
+  int act;              // MEHHUA_ACT_*
+  int mode;             // MEHHUA_MODE_*
   float score_thr, nms_iou, fg_thr, obj_thr, cluster_iou, lambda_scale, lambda_eps;
   float means[4], stds[4];
   float max_ratio;      // |ln(wh_ratio_clip)|
@@ -70,8 +72,9 @@ struct Workspace {
   int* k2_done;                // [kK2SplitPairs] arrival counters of split K2 pairs
   float* k2_part;              // [kK2SplitPairs, kK2Sub, C+1] partial class / entropy sums of split K2 pairs
   int* inv_map;                // [B, N]   position -> row of the dense top-k levels (-1 = not kept)
-  unsigned* fg_list;           // [B, pair_cap] Entropy_ALL: (level << 28 | prior) of every foreground prior
-  int* fg_cnt;                 // [B]
+  unsigned* fg_mask;           // [B, tiles_per_image, 4] Entropy_ALL: one foreground bit per prior (a ballot word per warp of a tile)
+  int* tile_cnt;               // [B, tiles_per_image] foreground priors of each tile
+  int* tile_pref;              // [B, tiles_per_image] exclusive prefix of tile_cnt inside the tile's (level, anchor) plane
   float* lam_part;             // [B, tiles_per_image] per-tile lambda sums (Entropy_ALL)
   float* tau;                  // [B, S]   capture threshold of a capture level (K1t)
   int* cap_cnt;                // [B, S]   rows captured so far / in total

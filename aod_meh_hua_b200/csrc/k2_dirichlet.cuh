@@ -451,7 +451,7 @@ k2_dirichlet_kernel(const __grid_constant__ Plan p, const float* __restrict__ sc
       a0 += __shfl_xor_sync(full, a0, o);
       nbad += __shfl_xor_sync(full, nbad, o);
     }
-    if (nbad > 0 && lane == 0) atomicOr(status, MEHHUA_ST_BAD_ALPHA);
+    if (nbad > 0 && lane == 0 && p.act != MEHHUA_ACT_RELU) atomicOr(status, MEHHUA_ST_BAD_ALPHA);   // relu rows have zeros by construction
     __syncwarp();
 
     const long long ioff = (inj != nullptr && inj_off != nullptr) ? inj_off[b * p.S + s] : -1;

@@ -84,8 +84,15 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   if (cfg->pair_cap < 1) return arg_fail("pair_cap must be positive");
   if (cfg->n_samples < 0) return arg_fail("n_samples must be >= 0 (0 = analytic form)");
   if (cfg->mode != MEHHUA_MODE_NMS && cfg->mode != MEHHUA_MODE_ALL) return arg_fail("mode");
-  for (int a : {cfg->agg_object, cfg->agg_scale, cfg->agg_class})
+  for (int a : {cfg->agg_object, cfg->agg_scale})
     if (a < MEHHUA_AGG_SUM || a > MEHHUA_AGG_MAX) return arg_fail("aggregation op");
+  if (cfg->agg_class < MEHHUA_AGG_SUM || cfg->agg_class > MEHHUA_AGG_POOL ||
+      (cfg->agg_class == MEHHUA_AGG_POOL && cfg->mode != MEHHUA_MODE_ALL))
+    return arg_fail("class aggregation op (MEHHUA_AGG_POOL needs MEHHUA_MODE_ALL)");
+  if (cfg->activation != MEHHUA_ACT_SOFTMAX &&
+      !(cfg->activation == MEHHUA_ACT_RELU_PLUS_ONE && cfg->mode == MEHHUA_MODE_NMS && cfg->head == MEHHUA_HEAD_RETINA) &&
+      !(cfg->activation == MEHHUA_ACT_RELU && cfg->mode == MEHHUA_MODE_ALL && cfg->head == MEHHUA_HEAD_RETINA))
+    return arg_fail("activation: relu_plus_one needs MODE_NMS + Retina head, relu needs MODE_ALL + Retina head");
   Plan p;
   memset(&p, 0, sizeof(p));
   p.S = cfg->num_levels; p.B = B; p.C = cfg->c_out; p.head = cfg->head;
@@ -129,7 +136,7 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
   p.nms_pre = cfg->nms_pre; p.max_per_img = cfg->max_per_img; p.pair_cap = cfg->pair_cap;
   p.n_samples = cfg->n_samples; p.use_lambda = cfg->use_lambda;
   p.agg_object = cfg->agg_object; p.agg_scale = cfg->agg_scale; p.agg_class = cfg->agg_class;
-  p.cls_w = cfg->cls_w; p.rescale = cfg->rescale;
+  p.cls_w = cfg->cls_w; p.rescale = cfg->rescale; p.act = cfg->activation; p.mode = cfg->mode;
   p.score_thr = cfg->score_thr; p.nms_iou = cfg->nms_iou; p.fg_thr = cfg->fg_thr;
   p.obj_thr = cfg->obj_thr; p.cluster_iou = cfg->cluster_iou;
   p.lambda_scale = cfg->lambda_scale; p.lambda_eps = cfg->lambda_eps;
@@ -155,8 +162,10 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   const size_t o_cnt = take((size_t)p.B * sizeof(int));
   const size_t o_maxc = take((size_t)p.B * sizeof(unsigned));
   const size_t o_inv = take((size_t)p.B * p.N * sizeof(int));
-  const size_t o_fgl = take((size_t)p.B * p.pair_cap * sizeof(unsigned));
-  const size_t o_fgc = take((size_t)p.B * sizeof(int));
+  const bool all_mode = p.mode == MEHHUA_MODE_ALL;      // Entropy_ALL family: foreground bit masks, tile counts and prefixes
+  const size_t o_fgm = take(all_mode ? (size_t)p.B * p.tiles_per_image * (kK1aThreads / 32) * sizeof(unsigned) : 0);
+  const size_t o_tcnt = take(all_mode ? (size_t)p.B * p.tiles_per_image * sizeof(int) : 0);
+  const size_t o_tpre = take(all_mode ? (size_t)p.B * p.tiles_per_image * sizeof(int) : 0);
   const size_t o_lamp = take((size_t)p.B * p.tiles_per_image * sizeof(float));
   const size_t o_tau = take((size_t)p.B * p.S * sizeof(float));
   const size_t o_capc = take((size_t)p.B * p.S * sizeof(int));
@@ -174,8 +183,9 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
     ws->k2_done = reinterpret_cast<int*>(b + o_k2done);
     ws->k2_part = reinterpret_cast<float*>(b + o_k2part);
     ws->inv_map = reinterpret_cast<int*>(b + o_inv);
-    ws->fg_list = reinterpret_cast<unsigned*>(b + o_fgl);
-    ws->fg_cnt = reinterpret_cast<int*>(b + o_fgc);
+    ws->fg_mask = reinterpret_cast<unsigned*>(b + o_fgm);
+    ws->tile_cnt = reinterpret_cast<int*>(b + o_tcnt);
+    ws->tile_pref = reinterpret_cast<int*>(b + o_tpre);
     ws->lam_part = reinterpret_cast<float*>(b + o_lamp);
     ws->tau = reinterpret_cast<float*>(b + o_tau);
     ws->cap_cnt = reinterpret_cast<int*>(b + o_capc);
@@ -320,16 +330,18 @@ int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const
   }
 }
 
-template <int C, int HEAD>
+template <int C, int HEAD, int ACT>
 int launch_all_typed(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
-  ka_fg_kernel<C, HEAD><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
-      p, ws.fg_list, ws.fg_cnt, ws.lam_part, ws.status, reinterpret_cast<unsigned*>(o->level_maxconf));
+  ka_fg_kernel<C, HEAD, ACT><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
+      p, ws.fg_mask, ws.tile_cnt, ws.lam_part, reinterpret_cast<unsigned*>(o->level_maxconf));
   LAUNCHED("ka_fg_kernel");
-  if (int rc = ensure_dyn_smem(ka_finalize_kernel<C, HEAD>, kAllSmem)) return rc;
-  ka_finalize_kernel<C, HEAD><<<p.B, kAllThreads, kAllSmem, st>>>(
-      p, ws.fg_list, ws.fg_cnt, ws.lam_part, o->score_rows, o->lam_rows, o->topk_idx, o->row_max, o->row_argmax,
-      o->level_fg, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off, o->lam_mean, o->n_obj, o->n_det, ws.status);
-  LAUNCHED("ka_finalize_kernel");
+  ka_scan_kernel<<<p.B, kAllScanThreads, 0, st>>>(p, ws.tile_cnt, ws.tile_pref, ws.lam_part, o->pair_off, o->level_fg,
+                                                  o->lam_mean, o->n_obj, o->n_det, ws.status);
+  LAUNCHED("ka_scan_kernel");
+  ka_rows_kernel<C, HEAD, ACT><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
+      p, ws.fg_mask, ws.tile_cnt, ws.tile_pref, o->pair_off, o->score_rows, o->lam_rows, o->topk_idx, o->row_max,
+      o->row_argmax, o->pair_row, o->pair_obj, o->pair_cls);
+  LAUNCHED("ka_rows_kernel");
   return 0;
 }
 
@@ -337,20 +349,36 @@ int launch_all(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cu
   if (!o || !o->score_rows || !o->lam_rows || !o->topk_idx || !o->row_max || !o->row_argmax || !o->level_fg ||
       !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->lam_mean || !o->n_obj || !o->n_det)
     return arg_fail("null Entropy_ALL buffer");
-  CU(cudaMemsetAsync(ws.fg_cnt, 0, (size_t)p.B * sizeof(int), st));
   if (o->level_maxconf) CU(cudaMemsetAsync(o->level_maxconf, 0, (size_t)p.B * p.S * sizeof(float), st));
   if (p.head == MEHHUA_HEAD_RETINA) {
+    if (p.act == MEHHUA_ACT_RELU) {
+      switch (p.C) {
+        case 20: return launch_all_typed<20, MEHHUA_HEAD_RETINA, MEHHUA_ACT_RELU>(p, ws, o, st);
+        case 80: return launch_all_typed<80, MEHHUA_HEAD_RETINA, MEHHUA_ACT_RELU>(p, ws, o, st);
+        default: return launch_all_typed<0, MEHHUA_HEAD_RETINA, MEHHUA_ACT_RELU>(p, ws, o, st);
+      }
+    }
     switch (p.C) {
-      case 20: return launch_all_typed<20, MEHHUA_HEAD_RETINA>(p, ws, o, st);
-      case 80: return launch_all_typed<80, MEHHUA_HEAD_RETINA>(p, ws, o, st);
-      default: return launch_all_typed<0, MEHHUA_HEAD_RETINA>(p, ws, o, st);
+      case 20: return launch_all_typed<20, MEHHUA_HEAD_RETINA, MEHHUA_ACT_SOFTMAX>(p, ws, o, st);
+      case 80: return launch_all_typed<80, MEHHUA_HEAD_RETINA, MEHHUA_ACT_SOFTMAX>(p, ws, o, st);
+      default: return launch_all_typed<0, MEHHUA_HEAD_RETINA, MEHHUA_ACT_SOFTMAX>(p, ws, o, st);
     }
   }
   switch (p.C) {
-    case 21: return launch_all_typed<21, MEHHUA_HEAD_SSD>(p, ws, o, st);
-    case 81: return launch_all_typed<81, MEHHUA_HEAD_SSD>(p, ws, o, st);
-    default: return launch_all_typed<0, MEHHUA_HEAD_SSD>(p, ws, o, st);
+    case 21: return launch_all_typed<21, MEHHUA_HEAD_SSD, MEHHUA_ACT_SOFTMAX>(p, ws, o, st);
+    case 81: return launch_all_typed<81, MEHHUA_HEAD_SSD, MEHHUA_ACT_SOFTMAX>(p, ws, o, st);
+    default: return launch_all_typed<0, MEHHUA_HEAD_SSD, MEHHUA_ACT_SOFTMAX>(p, ws, o, st);
   }
+}
+
+int launch_all_reduce(const Plan& p, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (!o || !o->pair_cls || !o->pair_off || !o->pair_unc || !o->image_scores) return arg_fail("null Entropy_ALL buffer");
+  const size_t smem = ka_reduce_smem_bytes(p.S, p.C);
+  if (smem > 227 * 1024) return arg_fail("c_out too large for the Entropy_ALL reduce kernel");
+  if (int rc = ensure_dyn_smem(ka_reduce_kernel, smem)) return rc;
+  ka_reduce_kernel<<<p.B, kAllAggThreads, smem, st>>>(p, o->pair_cls, o->pair_off, o->pair_unc, o->image_scores, o->group_unc);
+  LAUNCHED("ka_reduce_kernel");
+  return 0;
 }
 
 int launch_nms(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
@@ -424,6 +452,7 @@ int launch_k2(const Plan& p, const Workspace& ws, const int64_t* image_ids, cons
 }
 
 int launch_hua(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
+  if (p.mode == MEHHUA_MODE_ALL) return launch_all_reduce(p, o, st);     // Entropy_ALL family: (level, class) means, any count
   if (!o || !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->pair_unc || !o->n_obj ||
       !o->image_scores)
     return arg_fail("null HUA buffer");
@@ -484,6 +513,7 @@ int mehhua_read_status(const mehhua_config_t* cfg, const mehhua_level_t* levels,
 int mehhua_k1_alpha_topk(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
                          const float* img_shapes, const float* scale_factors, const mehhua_buffers_t* out,
                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->mode != MEHHUA_MODE_NMS) return arg_fail("cfg->mode must be MEHHUA_MODE_NMS for this entry point");
   Prepared pr;
   int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
   if (rc) return rc;
@@ -492,6 +522,7 @@ int mehhua_k1_alpha_topk(const mehhua_config_t* cfg, const mehhua_level_t* level
 
 int mehhua_nms_objects(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
                        const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->mode != MEHHUA_MODE_NMS) return arg_fail("cfg->mode must be MEHHUA_MODE_NMS for this entry point");
   Prepared pr;
   int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
   if (rc) return rc;
@@ -500,6 +531,7 @@ int mehhua_nms_objects(const mehhua_config_t* cfg, const mehhua_level_t* levels,
 
 int mehhua_iou_pairs(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
                      const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->mode != MEHHUA_MODE_NMS) return arg_fail("cfg->mode must be MEHHUA_MODE_NMS for this entry point");
   Prepared pr;
   int rc = prepare(cfg, levels, B, false, workspace, workspace_bytes, stream, &pr);
   if (rc) return rc;
@@ -526,6 +558,7 @@ int mehhua_k3_hua(const mehhua_config_t* cfg, const mehhua_level_t* levels, int3
 int mehhua_score_batch(const mehhua_config_t* cfg, const mehhua_level_t* levels, int32_t B,
                        const float* img_shapes, const float* scale_factors, const int64_t* image_ids,
                        const mehhua_buffers_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->mode != MEHHUA_MODE_NMS) return arg_fail("cfg->mode must be MEHHUA_MODE_NMS for this entry point");
   Prepared pr;
   int rc = prepare(cfg, levels, B, true, workspace, workspace_bytes, stream, &pr);
   if (rc) return rc;
@@ -676,6 +709,7 @@ int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* lev
   int rc = check_device();
   if (rc) return rc;
   if (!ctx_out) return arg_fail("null ctx_out");
+  if (cfg && cfg->mode != MEHHUA_MODE_NMS) return arg_fail("the host-buffer context serves the Entropy_NMS route: cfg->mode must be MEHHUA_MODE_NMS");
   Plan p;
   if ((rc = build_plan(cfg, level_shapes, max_batch, false, &p))) return rc;
   mehhua_host_ctx* c = new (std::nothrow) mehhua_host_ctx();
@@ -731,6 +765,7 @@ int mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* lev
   b.image_scores = reinterpret_cast<float*>(a + o_sc);
   b.level_maxconf = nullptr;               // getMaxConf is not part of the host-buffer call
   b.pair_avg = nullptr;
+  b.group_unc = nullptr;
   c->img_shapes = reinterpret_cast<float*>(a + o_shp);
   c->scale_factors = reinterpret_cast<float*>(a + o_sf);
   c->image_ids = reinterpret_cast<int64_t*>(a + o_ids);

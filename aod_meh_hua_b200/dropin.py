@@ -58,6 +58,8 @@ class B200ScoringMixin:
     # MyLSSDHead ignore those kwargs and hard-code 0.3 / 0.5 (Lambda_L2.py:349, 500, 508)
     mehhua_thresholds_from_kwargs = False
     mehhua_fused_eval = True            # isEval route: detections from K1 + K3a instead of super()
+    mehhua_all_pair_cap = None          # Entropy_ALL / Entropy_Avg: foreground priors per image the row buffers hold
+                                        # (None = min(N, 32768); raise it up to N for heads with very many of them)
     _mehhua_scorers: Dict[tuple, Scorer]
 
     def _mehhua_scorer(self, cls_scores: List[torch.Tensor], img_hw, uPool2: str, clsW: bool, kwargs=None) -> Scorer:
@@ -90,8 +92,9 @@ class B200ScoringMixin:
                     rescale=False, with_nms=True, **kwargs):
         scoring = bool(kwargs.get("isUnc")) and kwargs.get("uPool") == "Entropy_NMS" and with_nms \
             and "L_scores" in kwargs and not torch.onnx.is_in_onnx_export()
-        if bool(kwargs.get("isUnc")) and kwargs.get("uPool") == "Entropy_ALL" and not with_nms \
-                and "L_scores" in kwargs and (cfg is None or cfg is self.test_cfg):
+        if bool(kwargs.get("isUnc")) and "L_scores" in kwargs and (cfg is None or cfg is self.test_cfg) and (
+                (kwargs.get("uPool") == "Entropy_ALL" and not with_nms) or
+                (kwargs.get("uPool") == "Entropy_Avg" and self.mehhua_thresholds_from_kwargs)):
             return self._mehhua_entropy_all(mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes,
                                             scale_factors, **kwargs)
         if (not kwargs.get("isUnc")) and with_nms and self.mehhua_fused_eval and (cfg is None or cfg is self.test_cfg) \
@@ -128,26 +131,36 @@ class B200ScoringMixin:
 
     def _mehhua_entropy_all(self, mlvl_cls_scores, mlvl_bbox_preds, mlvl_anchors, img_shapes, scale_factors,
                             **kwargs):
-        """Entropy_ALL route (Lambda_L2.py:281-283, 362-365 -> ComputeScaleUnc + AggregateScaleUnc):
-        returns (det_results, AggedUnc).  The reference's det_results on this route are the raw
-        (boxes [N,4], scores [N,C+1]) of every prior, which no caller reads (apis/test.py:116 only
-        takes len()); they are returned here with zero rows."""
-        if kwargs.get("scaleUnc"):
-            raise NotImplementedError("scaleUnc output of the Entropy_ALL route")
+        """Entropy_ALL route (Lambda_L2.py:281-283, 362-365 -> ComputeScaleUnc + AggregateScaleUnc) and, for the
+        ablation heads, the Entropy_Avg route (Lambda_L2_ReLU.py:261-263 -> ComputeAvgUnc + AggregateAvgUnc):
+        returns (det_results, AggedUnc) or, with scaleUnc=True on Entropy_ALL, (det_results, AggedUnc, scaleUnc)
+        where scaleUnc[i][s] = {str(cls): (aleatoric, epistemic)} as ComputeScaleUnc builds it (Lambda_L2.py:377-378).
+        The reference's det_results on the Entropy_ALL route are the raw (boxes [N,4], scores [N,C+1]) of every
+        prior, which no caller reads (apis/test.py:116 only takes len()); they are returned here with zero rows."""
+        avg_mode = kwargs.get("uPool") == "Entropy_Avg"
+        if kwargs.get("scaleUnc") and avg_mode:
+            raise NotImplementedError("scaleUnc=True is undefined on the Entropy_Avg route of the reference")
         B = mlvl_cls_scores[0].shape[0]
         dev = mlvl_cls_scores[0].device
         hw = tuple(int(v) for v in img_shapes[0][:2])
         featmaps = [tuple(c.shape[-2:]) for c in mlvl_cls_scores]
         c_out = int(self.cls_out_channels)
         num_anchors = [c.shape[1] // c_out for c in mlvl_cls_scores]
-        key = ("all", tuple(featmaps), tuple(num_anchors), c_out, str(dev), kwargs["uPool2"], max(B, self.mehhua_max_batch))
+        agg = "Entropy_Avg" if avg_mode else kwargs["uPool2"]
+        key = ("all", tuple(featmaps), tuple(num_anchors), c_out, str(dev), agg, max(B, self.mehhua_max_batch),
+               self.mehhua_all_pair_cap)
         cache = self.__dict__.setdefault("_mehhua_scorers", {})
         if key not in cache:
             spec = _spec_from_head(self, featmaps, num_anchors, hw)
             p = self.mehhua_params
-            params = ScoringParams(n_samples=p.n_samples, fg_thr=p.fg_thr, lambda_scale=p.lambda_scale,
-                                   lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, agg=kwargs["uPool2"], seed=p.seed)
-            cache[key] = Scorer(spec, params, max_batch=max(B, self.mehhua_max_batch), device=dev, mode="all")
+            if avg_mode:     # ComputeAvgUnc: alpha = relu(logits) * lambda', T = 50, thresholds hard-coded (Lambda_L2_ReLU.py:453-466)
+                params = ScoringParams(n_samples=50, fg_thr=0.3, lambda_scale=p.lambda_scale, lambda_eps=p.lambda_eps,
+                                       use_lambda=True, agg=agg, seed=p.seed, activation="relu")
+            else:
+                params = ScoringParams(n_samples=p.n_samples, fg_thr=p.fg_thr, lambda_scale=p.lambda_scale,
+                                       lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, agg=agg, seed=p.seed)
+            cache[key] = Scorer(spec, params, max_batch=max(B, self.mehhua_max_batch), device=dev, mode="all",
+                                pair_cap=self.mehhua_all_pair_cap)
         sc = cache[key]
         ids = kwargs.get("image_ids")
         if ids is None and "batchIdx" in kwargs:
@@ -158,6 +171,11 @@ class B200ScoringMixin:
         dets = [(torch.zeros(0, 4, device=dev), torch.zeros(0, c_out + (0 if getattr(self, "last_activation", "relu") == "softmax" else 1), device=dev))
                 for _ in range(B)]
         agged = [float(v) if v != 0 else 0 for v in res.image_scores.cpu().tolist()]
+        if kwargs.get("scaleUnc"):
+            g = res.group_unc.cpu()
+            scale_unc = [[{f"{c}": (g[b, s, c, 1], g[b, s, c, 2]) for c in range(c_out) if g[b, s, c, 0] > 0}
+                          for s in range(g.shape[1])] for b in range(B)]
+            return dets, agged, scale_unc
         if kwargs.get("saveMaxConf"):
             return dets, agged, res.level_maxconf.max(dim=1)[0].tolist()
         return dets, agged
@@ -248,19 +266,25 @@ def calculate_uncertainty(cfg, model, data_loader, **kwargs):
     not swallow a failing batch (apis/test.py:122-128 would silently misalign image indices)."""
     if cfg.uncertainty_pool == "Random":     # Uncertainty_fns.Random (apis/test.py:20-25)
         return torch.randperm(len(data_loader.dataset)).numpy()
-    if cfg.uncertainty_pool not in ("Entropy_NMS", "Entropy_ALL"):     # apis/test.py:27-38, 52-63: one loop for both
-        raise NotImplementedError(f"uncertainty_pool={cfg.uncertainty_pool!r}: Entropy_NMS / Entropy_ALL / Random")
+    if cfg.uncertainty_pool not in ("Entropy_NMS", "Entropy_ALL", "Entropy_Avg"):     # apis/test.py:27-38, 52-63: one loop for all
+        raise NotImplementedError(f"uncertainty_pool={cfg.uncertainty_pool!r}: Entropy_NMS / Entropy_ALL / Entropy_Avg / Random")
     if "scaleUnc" not in kwargs:
         raise KeyError("scaleUnc")          # the reference reads kwargs['scaleUnc'] unconditionally (:129)
     model.eval()
     uncertainties, maxconfs = [], []
+    seen = 0        # running image offset: the Philox streams are keyed by the image's position in the pool, whatever
+                    # the batch sizes (a short last batch must not reuse the ids of earlier images)
     with torch.no_grad():
         for i, data in enumerate(data_loader):
             data = dict(data)
             data["img"] = getattr(data["img"], "data", data["img"])
             data["img_metas"] = getattr(data["img_metas"], "data", data["img_metas"])
+            metas = data["img_metas"][0] if isinstance(data["img_metas"], (list, tuple)) else data["img_metas"]
+            nb = len(metas)
+            extra = {} if "image_ids" in kwargs else {"image_ids": list(range(seen, seen + nb))}
             result, *unc = model(return_loss=False, rescale=True, isEval=False, batchIdx=i, isUnc=cfg.uncertainty_type,
-                                 uPool=cfg.uncertainty_pool, uPool2=cfg.uncertainty_pool2, **data, **kwargs)
+                                 uPool=cfg.uncertainty_pool, uPool2=cfg.uncertainty_pool2, **data, **kwargs, **extra)
+            seen += nb
             others = unc[1:]
             unc = unc[0]
             while isinstance(unc[0], list):

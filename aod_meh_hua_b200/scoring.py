@@ -43,6 +43,7 @@ def make_config(spec: DetectorSpec, params: ScoringParams, pair_cap: int, rescal
     cfg.wh_ratio_clip = 16 / 1000
     cfg.rescale = int(rescale)
     cfg.pair_cap = pair_cap
+    cfg.activation = params.activation_code
     cfg.seed = params.seed
     return cfg
 
@@ -71,6 +72,7 @@ class BatchResult:
     pair_unc: torch.Tensor
     image_scores: torch.Tensor
     level_maxconf: torch.Tensor
+    group_unc: Optional[torch.Tensor] = None      # Entropy_ALL family only
 
 
 class Scorer:
@@ -92,7 +94,7 @@ class Scorer:
         self.mode = mode
         K = spec.k_tot
         if pair_cap is None:
-            pair_cap = min(K * spec.max_per_img, 65536) if mode == "nms" else min(spec.num_priors, 16384)
+            pair_cap = min(K * spec.max_per_img, 65536) if mode == "nms" else min(spec.num_priors, 32768)
         self.pair_cap = int(pair_cap)
         self.cfg = make_config(spec, self.params, self.pair_cap, rescale, mode)
         self._shape_levels = _lib.LevelArray()
@@ -115,6 +117,8 @@ class Scorer:
             pair_cls=torch.zeros(B, P, **i32), pair_off=torch.zeros(B, S + 1, **i32),
             lam_mean=torch.zeros(B, S, **f32), pair_unc=torch.zeros(B, P, 3, **f32),
             image_scores=torch.zeros(B, **f32), level_maxconf=torch.zeros(B, S, **f32))
+        if mode == "all":        # per (level, class): count, mean aleatoric, mean epistemic (the scaleUnc return item)
+            self.t["group_unc"] = torch.zeros(B, S, Cc, 3, **f32)
         self.bufs = _lib.Buffers()
         for name in _lib.BUFFER_FIELDS:
             if name in self.t:
@@ -275,8 +279,10 @@ class Scorer:
         """Raise on data-dependent failures; returns the informational bits."""
         st = self.read_status()
         if st & _lib.ST_PAIR_OVERFLOW:
-            raise _lib.MehhuaError(f"an image produced more than pair_cap={self.pair_cap} (box, object) pairs; "
-                                   "re-create the Scorer with a larger pair_cap")
+            what = "foreground priors" if self.mode == "all" else "(box, object) pairs"
+            limit = self.spec.num_priors if self.mode == "all" else self.spec.k_tot * self.spec.max_per_img
+            raise _lib.MehhuaError(f"an image produced more than pair_cap={self.pair_cap} {what}; re-create the "
+                                   f"Scorer with a larger pair_cap (at most {limit} can occur for this geometry)")
         return st
 
     def detect(self, cls_scores, bbox_preds, anchors, img_shapes, scale_factors):

@@ -20,6 +20,9 @@ HEAD_RETINA = 0  # Lambda_L2Net: C_out = num_classes, score = p / (sum(p)+1e-20+
 HEAD_SSD = 1     # MyLSSDHead:  C_out = num_classes + 1 (background last), score = p
 
 AGG_SUM, AGG_AVG, AGG_MAX = 0, 1, 2
+AGG_POOL = 3      # class axis of the Entropy_ALL family only: no class split (Entropy_Avg)
+ACT_SOFTMAX, ACT_RELU_PLUS_ONE, ACT_RELU = 0, 1, 2
+_ACTIVATIONS = {"softmax": ACT_SOFTMAX, "relu_plus_one": ACT_RELU_PLUS_ONE, "relu": ACT_RELU}
 _AGG_TOKENS = {"Sum": AGG_SUM, "Avg": AGG_AVG, "Max": AGG_MAX}
 
 
@@ -49,6 +52,8 @@ def parse_scale_agg(kind: str) -> Tuple[int, int, int]:
     (Lambda_L2.py:636-691) hard-codes exactly four types; there is a single pseudo-object, so the
     object reducer is Sum.  (The reference silently returns an empty list for any other string,
     which crashes its caller later; here it is a ValueError.)"""
+    if kind == "Entropy_Avg":        # ComputeAvgUnc / AggregateAvgUnc (Lambda_L2_ReLU.py:446-474, 532-541): pooled level means, mean over levels
+        return AGG_SUM, AGG_AVG, AGG_POOL
     if kind not in _SCALE_TYPES:
         raise ValueError(f"unknown Entropy_ALL aggregation type {kind!r}; one of {sorted(_SCALE_TYPES)}")
     sc, cl = _SCALE_TYPES[kind]
@@ -192,3 +197,10 @@ class ScoringParams:
     agg: str = "objectSum_scaleMax_classSum"   # Config_RetinaNet.py:18
     cls_w: bool = False             # tools/train_RetinaNet.py:30 clsW
     seed: int = 20                  # tools/train_RetinaNet.py:80-87
+    # how a class row is formed from the logits: "softmax" (the scoring heads), "relu_plus_one" (the base head's
+    # evidential form, L_anchor_head.py:401-406; detection route), "relu" (Entropy_Avg, Lambda_L2_ReLU.py:453-455)
+    activation: str = "softmax"
+
+    @property
+    def activation_code(self) -> int:
+        return _ACTIVATIONS[self.activation]

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MEHHUA_ABI_VERSION 4
+#define MEHHUA_ABI_VERSION 5
 #define MEHHUA_MAX_LEVELS 8
 #define MEHHUA_MAX_DETS 256      /* upper bound on max_per_img */
 #define MEHHUA_MAX_NMS_PRE 4096  /* upper bound on nms_pre */
@@ -61,6 +61,15 @@ extern "C" {
 #define MEHHUA_AGG_SUM 0
 #define MEHHUA_AGG_AVG 1
 #define MEHHUA_AGG_MAX 2
+#define MEHHUA_AGG_POOL 3  /* agg_class only, MEHHUA_MODE_ALL only: no class split - the mean over ALL foreground priors
+                              of a level (ComputeAvgUnc / AggregateAvgUnc, Lambda_L2_ReLU.py:446-474, 532-541) */
+
+/* how a row of class values is formed from the logits */
+#define MEHHUA_ACT_SOFTMAX       0  /* the scoring heads: p = softmax(logits) (Lambda_L2.py:269-273, My_L_ssd_head.py:331) */
+#define MEHHUA_ACT_RELU_PLUS_ONE 1  /* MEHHUA_MODE_NMS, Retina head: alpha = relu(logits) + 1, score = alpha / (sum alpha + 1e-20)
+                                       - the base head's evidential form (L_anchor_head.py:401-406); detection route */
+#define MEHHUA_ACT_RELU          2  /* MEHHUA_MODE_ALL, Retina head: row = relu(logits), FG = max(row / (sum + 1e-9)) > fg_thr,
+                                       alpha = row * lambda' (zeros allowed) - uncertainty_pool 'Entropy_Avg' */
 
 typedef struct mehhua_level {
   const float* logits;
@@ -97,6 +106,7 @@ typedef struct mehhua_config {
   int32_t rescale;         /* divide boxes by scale_factor (Lambda_L2.py:307-308) */
   int32_t pair_cap;        /* capacity of the per-image pair list */
   int32_t mode;            /* MEHHUA_MODE_*: which uncertainty_pool route the buffers are used for */
+  int32_t activation;      /* MEHHUA_ACT_* (0 = softmax, the scoring heads' form) */
   uint64_t seed;           /* Philox key of the free-running sampler */
 } mehhua_config_t;
 
@@ -124,6 +134,9 @@ typedef struct mehhua_buffers {
   float*   level_maxconf;/* [B, S] or NULL     max over ALL priors of max_c softmax: the `output`   *
                           *                    of getMaxConf (utils/functions.py:467-476); fused   *
                           *                    into the logits pass (K1a / KA1), NULL = skipped     */
+  float*   group_unc;    /* [B, S, C_out, 3] or NULL, MEHHUA_MODE_ALL: per (level, class) the number of foreground priors, *
+                          *                    their mean aleatoric and mean epistemic uncertainty - the `scaleUnc`    *
+                          *                    third return item of _get_bboxes (Lambda_L2.py:377-378)                  */
   float*   pair_avg;     /* [B, pair_cap, C_out] or NULL: mean_t x_c of every pair (`avg` of Lambda_L2.py:521),  *
                           *                    a diagnostic output of K2 for the per-class moment tests     */
 } mehhua_buffers_t;

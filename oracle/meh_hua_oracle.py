@@ -28,6 +28,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch.distributions import Dirichlet
 
 HEAD_RETINA, HEAD_SSD = 0, 1
@@ -409,6 +410,65 @@ def aggregate_scale_unc(nested, kind: str):
                 per_lvl.append(f_cls(np.array(vals)))
         out.append(f_scale(np.array(per_lvl)) if per_lvl else 0)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Entropy_Avg mode of the ablation heads - ComputeAvgUnc + AggregateAvgUnc
+#                                                  (Lambda_L2_ReLU.py:446-474, 532-541)
+# --------------------------------------------------------------------------------------------
+def zero_alpha_sampler(alpha: torch.Tensor, T: int, i: int, s: int) -> torch.Tensor:
+    """Dirichlet draws for rows that contain alpha == 0 (relu of a negative logit).  The reference was
+    pinned to torch 1.5, which sampled such rows silently (a zero-shape gamma draw is 0 and the sample
+    is clamped to FLT_MIN); later torch versions refuse them unless argument validation is off."""
+    return Dirichlet(alpha, validate_args=False).sample(torch.tensor([T]))
+
+
+def compute_avg_unc(cls_scores: List[torch.Tensor], L_scores: List[torch.Tensor], *, c_out: int, T: int = 50,
+                    fg_thr: float = 0.3, lambda_scale: float = 25.0, lambda_eps: float = 1e-7,
+                    sampler: SampleFn = zero_alpha_sampler):
+    """r = relu(logits); prob = r / (sum r + 1e-9); every prior with max prob > fg_thr is sampled with
+    alpha = r * lambda' (T = 50); output[i][s] = mean epistemic uncertainty of the level's foreground
+    priors ({} when it has none).  Returns (nested, flat)."""
+    S = len(cls_scores)
+    B = cls_scores[0].shape[0]
+    nested = [[{} for _ in range(S)] for _ in range(B)]
+    flat = []
+    for s in range(S):
+        for i in range(B):
+            x = cls_scores[s][i].permute(1, 2, 0).reshape(-1, c_out)
+            r = F.relu(x)
+            prob = r / (r.sum(dim=1, keepdim=True) + 1e-9)
+            fg = prob.max(dim=1)[0] > fg_thr
+            if not bool(fg.any()):
+                continue
+            lam = L_scores[s][i].permute(1, 2, 0).reshape(-1, 1)
+            lam_p = lam.mean() / (lam + lambda_eps) * lambda_scale
+            alpha = (r * lam_p)[fg]
+            smp = sampler(alpha, T, i, s)
+            total, ale, epi = uncertainty_from_samples(smp)
+            nested[i][s] = epi.mean().item()
+            flat.append(dict(image=i, level=s, prior=fg.nonzero()[:, 0].numpy(), cls=alpha.argmax(dim=1).numpy(),
+                             alpha=alpha.numpy(), total=total.numpy(), ale=ale.numpy(), epi=epi.numpy()))
+    return nested, flat
+
+
+def aggregate_avg_unc(nested):
+    """AggregateAvgUnc: the mean over the levels that hold a (truthy) value; NaN when none does."""
+    out = []
+    for img in nested:
+        vals = [v for v in img if v]
+        with np.errstate(invalid="ignore"), __import__("warnings").catch_warnings():
+            __import__("warnings").simplefilter("ignore")
+            out.append(np.array(vals).mean())
+    return out
+
+
+def score_batch_avg(batch: Dict[str, object], *, c_out: int, T: int = 50, fg_thr: float = 0.3,
+                    lambda_scale: float = 25.0, lambda_eps: float = 1e-7, sampler: SampleFn = zero_alpha_sampler,
+                    **_unused) -> Dict[str, object]:
+    nested, flat = compute_avg_unc(batch["cls_scores"], batch["L_scores"], c_out=c_out, T=T, fg_thr=fg_thr,
+                                   lambda_scale=lambda_scale, lambda_eps=lambda_eps, sampler=sampler)
+    return dict(nested=nested, flat=flat, image_scores=aggregate_avg_unc(nested))
 
 
 def score_batch_all(batch: Dict[str, object], *, head: int, c_out: int, T: int = 500, fg_thr: float = 0.3,

@@ -18,13 +18,14 @@ def make_batch(spec_name: str, gids, seed0: int = 20, scale_factor=(1.0, 1.0, 1.
 class Recorder:
     """Sampler hook: draws with torch (seeded) and keeps alpha + samples per (image, level)."""
 
-    def __init__(self, seed: int = 1234):
+    def __init__(self, seed: int = 1234, sampler=None):
         self.gen_seed = seed
         self.blocks = {}
+        self.sampler = sampler or O.default_sampler
         torch.manual_seed(seed)
 
     def __call__(self, alpha, T, i, s):
-        smp = O.default_sampler(alpha, T, i, s)
+        smp = self.sampler(alpha, T, i, s)
         self.blocks[(i, s)] = (alpha.clone(), smp)
         return smp
 

@@ -84,6 +84,19 @@ def test_get_bboxes_route(spec_name):
     dets_all, unc_all = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam, **kw3)
     assert len(dets_all) == 2 and len(unc_all) == 2
     np.testing.assert_allclose(unc_all, np.asarray(want_all, dtype=np.float64), rtol=0.15, atol=0.03)
+    # scaleUnc=True: the third return item is ComputeScaleUnc's nested structure (Lambda_L2.py:377-378)
+    d3, u3, sc3 = head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam,
+                                   **dict(kw3, scaleUnc=True))
+    assert len(sc3) == 2 and all(len(img) == spec.num_levels for img in sc3)
+    torch.manual_seed(7)
+    nested = O.score_batch_all(batch, kind="scaleSum_classAvg", **O.spec_kwargs(spec, ScoringParams()))["nested"]
+    for b in range(2):
+        for s in range(spec.num_levels):
+            assert set(sc3[b][s].keys()) == set(nested[b][s].keys())
+            for c, (ale, epi) in sc3[b][s].items():
+                assert torch.is_tensor(epi) and epi.dim() == 0
+    # and the value the reference's AggregateScaleUnc makes of that structure is the returned score
+    np.testing.assert_allclose(O.aggregate_scale_unc(sc3, "scaleSum_classAvg"), u3, rtol=1e-5, atol=1e-6)
     with pytest.raises(ValueError):
         head._get_bboxes(cls, reg, anc, batch["img_shapes"], sf, None, True, False, L_scores=lam,
                          **dict(KW, uPool="Entropy_ALL", uPool2="objectSum_scaleMax_classSum"))

@@ -296,6 +296,117 @@ def test_entropy_all_mode_parity(spec_name, kind):
                                rtol=0.2, atol=0.03)
 
 
+def _check_all_mode(spec, batch, out, rec, sc, B, lam_alpha=None):
+    """Shared body: foreground prior lists in prior order, class keys, per-prior uncertainties under
+    injection against the oracle's flat records."""
+    S = spec.num_levels
+    res = sc.result()
+    poff = res.pair_off.cpu().numpy()
+    for b in range(B):
+        recs = sorted([r for r in out["flat"] if r["image"] == b], key=lambda r: r["level"])
+        n = poff[b, S]
+        assert n == sum(len(r["prior"]) for r in recs)
+        for r in recs:
+            a, e = poff[b, r["level"]], poff[b, r["level"] + 1]
+            assert np.array_equal(res.topk_idx[b, a:e].cpu().numpy(), r["prior"])
+            unc = res.pair_unc[b, a:e].cpu().numpy()
+            np.testing.assert_allclose(unc[:, 0], r["total"], rtol=RTOL, atol=2e-6)
+            np.testing.assert_allclose(unc[:, 1], r["ale"], rtol=RTOL, atol=2e-6)
+            np.testing.assert_allclose(unc[:, 2], r["epi"], rtol=1e-4, atol=5e-6)
+    return res
+
+
+def test_entropy_all_handles_any_number_of_foreground_priors():
+    """round 1 capped the Entropy_ALL route at 8192 / 16384 foreground priors per image
+    (a shared-memory sort).  Here more than half of a 49 104-prior image is foreground (the head has no
+    background class, so `max softmax > 0.3` can hold anywhere): 25 000+ rows per image, T = 8 samples
+    injected, every per-prior value and the image score against the oracle; the group table (the scaleUnc
+    return item) against the oracle's nested dicts."""
+    from oracle import meh_hua_oracle as O
+    from tests.helpers import Recorder
+    spec, batch = make_batch("cfg1_retina_r50_512_voc", [0, 1])
+    g = torch.Generator().manual_seed(3)
+    for s, t in enumerate(batch["cls_scores"]):            # push one class of ~55 % of the priors up
+        Bn, ch, h, w = t.shape
+        a = ch // spec.c_out
+        v = t.view(Bn, a, spec.c_out, h, w)
+        hit = torch.rand(Bn, a, h, w, generator=g) < 0.55
+        cls = torch.randint(0, spec.c_out, (Bn, a, h, w), generator=g)
+        v.scatter_add_(2, cls.unsqueeze(2), (hit.float() * 5.0).unsqueeze(2))
+    params = ScoringParams(agg="scaleSum_classAvg", n_samples=8)
+    rec = Recorder(5)
+    out = O.score_batch_all(batch, kind=params.agg, sampler=rec, **O.spec_kwargs(spec, params))
+    n_fg = [sum(len(r["prior"]) for r in out["flat"] if r["image"] == b) for b in range(2)]
+    assert min(n_fg) > 20000
+    sc = Scorer(spec, params, max_batch=2, device="cuda:0", mode="all", pair_cap=spec.num_priors)
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    sc.all_rows()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off)
+    sc.hua()
+    torch.cuda.synchronize()
+    assert sc.check_status() & 1 == 0
+    res = _check_all_mode(spec, batch, out, rec, sc, B)
+    np.testing.assert_allclose(res.image_scores.cpu().numpy(), np.asarray(out["image_scores"], dtype=np.float64),
+                               rtol=RTOL, atol=1e-5)
+    grp = res.group_unc.cpu().numpy()
+    for b in range(B):
+        for s in range(spec.num_levels):
+            want = out["nested"][b][s]
+            assert set(np.nonzero(grp[b, s, :, 0])[0].tolist()) == {int(c) for c in want}
+            for c, (ale, epi) in want.items():
+                np.testing.assert_allclose(grp[b, s, int(c), 1:], [float(ale), float(epi)], rtol=2e-5, atol=2e-6)
+    # a row buffer that is too small is reported, not silently truncated into a wrong score
+    small = Scorer(spec, params, max_batch=2, device="cuda:0", mode="all", pair_cap=4096)
+    small.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+               batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    small.all_rows()
+    with pytest.raises(Exception, match="pair_cap"):
+        small.check_status()
+
+
+@pytest.mark.parametrize("spec_name", ["tiny_retina_voc", "tiny_retina_c12", "cfg1_retina_r50_512_voc"])
+def test_entropy_avg_mode_parity(spec_name):
+    """Entropy_Avg route of the ablation heads (ComputeAvgUnc + AggregateAvgUnc, Lambda_L2_ReLU.py:446-474,
+    532-541): relu rows, FG = max(relu / (sum + 1e-9)) > 0.3, alpha = relu * lambda' (zeros allowed), T = 50,
+    per-level pooled mean, mean over levels - the oracle's draws injected."""
+    from oracle import meh_hua_oracle as O
+    from tests.helpers import Recorder
+    spec, batch = make_batch(spec_name, [0, 1, 2])
+    params = ScoringParams(agg="Entropy_Avg", n_samples=50, activation="relu")
+    rec = Recorder(9, sampler=O.zero_alpha_sampler)
+    out = O.score_batch_avg(batch, c_out=spec.c_out, T=50, sampler=rec)
+    assert sum(len(r["prior"]) for r in out["flat"]) > 0
+    sc = Scorer(spec, params, max_batch=3, device="cuda:0", mode="all")
+    B = sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"],
+                batch["img_shapes"], batch["scale_factors"], image_ids=batch["gids"])
+    sc.all_rows()
+    inj, off = injection_buffers(spec, rec, B, sc.device)
+    sc.k2(inj, off)
+    sc.hua()
+    torch.cuda.synchronize()
+    assert sc.check_status() & 1 == 0
+    res = _check_all_mode(spec, batch, out, rec, sc, B)
+    want = np.asarray(out["image_scores"], dtype=np.float64)
+    got = res.image_scores.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(got[~np.isnan(want)], want[~np.isnan(want)], rtol=RTOL, atol=1e-6)
+    # rows are relu(logits): alpha = row * lambda' matches the oracle's alpha, zeros included
+    S = spec.num_levels
+    poff = res.pair_off.cpu().numpy()
+    for r in out["flat"]:
+        b, a, e = r["image"], poff[r["image"], r["level"]], poff[r["image"], r["level"] + 1]
+        lam = res.lam_rows[b, a:e].cpu().numpy()
+        lam_p = res.lam_mean[b, r["level"]].item() / (lam + np.float32(1e-7)) * np.float32(25.0)
+        np.testing.assert_allclose(res.score_rows[b, a:e].cpu().numpy() * lam_p[:, None], r["alpha"], rtol=2e-5, atol=1e-12)
+    # free-running sampler end to end (T = 50: a noisy estimator on both sides)
+    res2 = sc.score(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                    batch["scale_factors"], image_ids=batch["gids"])
+    g2 = res2.image_scores.cpu().numpy()
+    np.testing.assert_allclose(g2[~np.isnan(want)], want[~np.isnan(want)], rtol=0.25, atol=0.03)
+
+
 @pytest.mark.parametrize("spec_name,gid", [("cfg3_retina_r50_800x1344_coco", 7), ("cfg4_ssd512_coco", 3),
                                            ("cfg1_retina_r50_512_voc", 5), ("cfg2_ssd300_voc", 11)])
 def test_full_size_configs_end_to_end(spec_name, gid):
