@@ -29,8 +29,34 @@ constexpr int kGatherThreads = 128;
 // (Retina; within 1 ulp of the reference's division) or p_c.
 // Summation is sequential in class order with explicitly rounded ops, so K1a (key) and K1c (row)
 // produce bit-identical values for the same prior.
+// Internal third head form: the Retina head with the base class's evidential scores (MEHHUA_ACT_RELU_PLUS_ONE,
+// L_anchor_head.py:401-406): alpha = relu(logit) + 1, S = sum alpha + 1e-20, score = alpha / S.  In this form
+// x[c] = alpha_c, `inv` carries S (the divisor, not a reciprocal) and den = 1.
+constexpr int kHeadRpo = 2;
+
+// score of one class from what softmax_regs / softmax_stream left behind
+template <int HEAD>
+__device__ __forceinline__ float k1_score(const float xc, const float inv, const float den) {
+  if (HEAD == kHeadRpo) return __fdiv_rn(xc, inv);
+  const float pc = __fmul_rn(xc, inv);
+  return (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
+}
+
 template <int C, int HEAD>
 __device__ __forceinline__ void softmax_regs(float (&x)[C], float& inv, float& den, float& pfg) {
+  if constexpr (HEAD == kHeadRpo) {
+    float sum = 0.f, mx = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      x[c] = __fadd_rn(fmaxf(x[c], 0.f), 1.f);
+      sum = __fadd_rn(sum, x[c]);
+      mx = fmaxf(mx, x[c]);
+    }
+    inv = __fadd_rn(sum, 1e-20f);
+    den = 1.f;
+    pfg = __fdiv_rn(mx, inv);
+    return;
+  }
   constexpr int CF = (HEAD == MEHHUA_HEAD_SSD) ? C - 1 : C;
   float mfg = x[0];
 #pragma unroll
@@ -60,6 +86,19 @@ __device__ __forceinline__ void softmax_regs(float (&x)[C], float& inv, float& d
 template <int HEAD>
 __device__ __forceinline__ void softmax_stream(const float* __restrict__ src, size_t stride, int C,
                                                float& m_out, float& inv, float& den, float& pfg) {
+  if constexpr (HEAD == kHeadRpo) {
+    float sum = 0.f, mx = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float a = __fadd_rn(fmaxf(__ldg(src + c * stride), 0.f), 1.f);
+      sum = __fadd_rn(sum, a);
+      mx = fmaxf(mx, a);
+    }
+    inv = __fadd_rn(sum, 1e-20f);
+    den = 1.f;
+    pfg = __fdiv_rn(mx, inv);
+    m_out = 0.f;
+    return;
+  }
   const int CF = (HEAD == MEHHUA_HEAD_SSD) ? C - 1 : C;
   float mfg = __ldg(src);
   for (int c = 1; c < CF; ++c) mfg = fmaxf(mfg, __ldg(src + c * stride));
@@ -145,7 +184,7 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
     key = k1_key<C, HEAD>(x, src, (size_t)L.HW, CC, inv, pfg, den);
     keys[(size_t)b * p.N + L.n_off + a * L.HW + hw] = key;
     if (pfg > p.fg_thr) level_fg[b * p.S + s] = 1;
-    if (level_maxconf) level_maxconf_update(level_maxconf + b * p.S + s, inv);
+    if (HEAD != kHeadRpo && level_maxconf) level_maxconf_update(level_maxconf + b * p.S + s, inv);
   }
   if constexpr (C > 0) {
     // capture: park the row of every prior at or above the level's threshold (about 1.75 k of them per
@@ -342,10 +381,7 @@ __device__ __forceinline__ void k1_row_body(const Plan& p, const LevelDev& L, co
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float sc = x[c];
-        if (!scores_ready) {
-          const float pc = __fmul_rn(x[c], inv);
-          sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
-        }
+        if (!scores_ready) sc = k1_score<HEAD>(x[c], inv, den);
         x[c] = sc;
         if (sc > best) { best = sc; arg = c; }
         if (c < NF && sc > p.score_thr) ++ncand;
@@ -357,9 +393,9 @@ __device__ __forceinline__ void k1_row_body(const Plan& p, const LevelDev& L, co
       softmax_stream<HEAD>(src, (size_t)L.HW, CC, m, inv, den, pfg);
       const float nml2 = -__fmul_rn(m, kLog2e);
       for (int c = 0; c < CC; ++c) {
-        const float e = ex2_approx(fmaf(__ldg(src + (size_t)c * L.HW), kLog2e, nml2));
-        const float pc = __fmul_rn(e, inv);
-        const float sc = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
+        const float lg = __ldg(src + (size_t)c * L.HW);
+        const float e = (HEAD == kHeadRpo) ? __fadd_rn(fmaxf(lg, 0.f), 1.f) : ex2_approx(fmaf(lg, kLog2e, nml2));
+        const float sc = k1_score<HEAD>(e, inv, den);
         tile_row[c] = sc;
         if (sc > best) { best = sc; arg = c; }
         if (c < NF && sc > p.score_thr) ++ncand;
@@ -509,10 +545,7 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
             inv = __ldcs(src + C); den = __ldcs(src + C + 1);
           }
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float pc = __fmul_rn(x[c], inv);
-            x[c] = (HEAD == MEHHUA_HEAD_RETINA) ? __fmul_rn(pc, den) : pc;
-          }
+          for (int c = 0; c < C; ++c) x[c] = k1_score<HEAD>(x[c], inv, den);
           parked = true;
         }
       }

@@ -316,6 +316,13 @@ int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const
   if (o->level_maxconf) CU(cudaMemsetAsync(o->level_maxconf, 0, (size_t)p.B * p.S * sizeof(float), st));
   CU(cudaMemsetAsync(ws.cand_cnt, 0, (size_t)p.B * sizeof(int), st));
   CU(cudaMemsetAsync(ws.cand_maxc, 0, (size_t)p.B * sizeof(unsigned), st));
+  if (p.head == MEHHUA_HEAD_RETINA && p.act == MEHHUA_ACT_RELU_PLUS_ONE) {
+    switch (p.C) {
+      case 20: return launch_k1_typed<20, kHeadRpo>(p, ws, img_shapes, scale_factors, o, st);
+      case 80: return launch_k1_typed<80, kHeadRpo>(p, ws, img_shapes, scale_factors, o, st);
+      default: return launch_k1_typed<0, kHeadRpo>(p, ws, img_shapes, scale_factors, o, st);
+    }
+  }
   if (p.head == MEHHUA_HEAD_RETINA) {
     switch (p.C) {
       case 20: return launch_k1_typed<20, MEHHUA_HEAD_RETINA>(p, ws, img_shapes, scale_factors, o, st);

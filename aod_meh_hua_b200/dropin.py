@@ -68,21 +68,21 @@ class B200ScoringMixin:
         if self.mehhua_thresholds_from_kwargs and kwargs:
             thr = kwargs.get("score_thr") or 0.3
             iou = kwargs.get("iou_thr") or 0.5
-            p = ScoringParams(n_samples=p.n_samples, fg_thr=thr, obj_thr=thr, cluster_iou=iou,
-                              lambda_scale=p.lambda_scale, lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, seed=p.seed)
+            p = ScoringParams(n_samples=p.n_samples, fg_thr=thr, obj_thr=thr, cluster_iou=iou, lambda_scale=p.lambda_scale,
+                              lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, seed=p.seed, activation=p.activation)
         featmaps = [tuple(c.shape[-2:]) for c in cls_scores]
         c_out = int(self.cls_out_channels)
         num_anchors = [c.shape[1] // c_out for c in cls_scores]
         device = cls_scores[0].device
         key = (tuple(featmaps), tuple(num_anchors), c_out, str(device), uPool2, bool(clsW),
-               max(B, self.mehhua_max_batch), p.fg_thr, p.obj_thr, p.cluster_iou)
+               max(B, self.mehhua_max_batch), p.fg_thr, p.obj_thr, p.cluster_iou, p.activation)
         cache = self.__dict__.setdefault("_mehhua_scorers", {})
         if key not in cache:
             spec = _spec_from_head(self, featmaps, num_anchors, img_hw)
             params = ScoringParams(n_samples=p.n_samples, fg_thr=p.fg_thr, obj_thr=p.obj_thr,
                                    cluster_iou=p.cluster_iou, lambda_scale=p.lambda_scale,
                                    lambda_eps=p.lambda_eps, use_lambda=p.use_lambda, agg=uPool2,
-                                   cls_w=bool(clsW), seed=p.seed)
+                                   cls_w=bool(clsW), seed=p.seed, activation=p.activation)
             parse_agg_spec(uPool2)       # KeyError for specs without object/scale/class, as the reference
             cache[key] = Scorer(spec, params, max_batch=max(B, self.mehhua_max_batch), device=device)
         return cache[key]
@@ -307,7 +307,7 @@ def calculate_uncertainty(cfg, model, data_loader, **kwargs):
 #   kwargs thresholds: Lambda_L2Net_ablation (Lambda_L2_ablation.py:  score_thr / iou_thr from kwargs, lambda' kept)
 #   kwargs thresholds, alpha = score row (no lambda'): Lambda_L2Net_NoL (Lambda_L2_noL.py), Lambda_L2Net_ReLU
 HEAD_VARIANTS = {
-    # registered name: (module, class, thresholds from kwargs, use_lambda)
+    # registered name: (module, class, thresholds from kwargs, use_lambda[, activation])
     "Lambda_L2Net_B200": ("Lambda_L2", "Lambda_L2Net", False, True),
     "Lambda_L1Net_B200": ("Lambda_L1", "Lambda_L1Net", False, True),
     "Lambda_MSLENet_B200": ("Lambda_MSLE", "Lambda_MSLENet", False, True),
@@ -316,14 +316,18 @@ HEAD_VARIANTS = {
     "Lambda_L2Net_NoL_B200": ("Lambda_L2_noL", "Lambda_L2Net_NoL", True, False),
     "Lambda_L2Net_ReLU_B200": ("Lambda_L2_ReLU", "Lambda_L2Net_ReLU", True, False),
     "MyLSSDHead_B200": ("My_L_ssd_head", "MyLSSDHead", False, True),
+    # the base head with last_activation='relu': no scoring route of its own, its detection route uses the
+    # evidential scores alpha = relu(logits) + 1 (L_anchor_head.py:401-406)
+    "L_AnchorHead_B200": ("L_anchor_head", "L_AnchorHead", False, True, "relu_plus_one"),
 }
 
 
 def make_variant(name: str, base: type) -> type:
     """The B200 drop-in class for one of the reference's scoring heads (`base` = the reference class)."""
-    _, _, from_kwargs, use_lambda = HEAD_VARIANTS[name]
+    _, _, from_kwargs, use_lambda, *rest = HEAD_VARIANTS[name]
     return type(name, (B200ScoringMixin, base), dict(
-        mehhua_thresholds_from_kwargs=from_kwargs, mehhua_params=ScoringParams(use_lambda=use_lambda)))
+        mehhua_thresholds_from_kwargs=from_kwargs,
+        mehhua_params=ScoringParams(use_lambda=use_lambda, activation=rest[0] if rest else "softmax")))
 
 
 def register_heads():
@@ -334,7 +338,7 @@ def register_heads():
     import importlib
     from mmdet.models.builder import HEADS
     out = {}
-    for name, (module, cls, _, _) in HEAD_VARIANTS.items():
+    for name, (module, cls, *_rest) in HEAD_VARIANTS.items():
         base = getattr(importlib.import_module(f"mmdet.models.dense_heads.{module}"), cls)
         out[name] = HEADS.register_module()(make_variant(name, base))
     return out

@@ -36,6 +36,8 @@ CASES = [
     ("retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
     ("retina_coco_aniso", "tiny_retina_coco", [3, 4], 20, 99, (1.07, 0.94, 1.07, 0.94), "objectAvg_scaleSum_classMax", True),
     ("ssd_voc", "tiny_ssd_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
+    # one BASELINE.json configuration at full size (config 1: RetinaNet R50-FPN 512x512, 20 VOC classes, 49 104 priors)
+    ("full_cfg1_retina_voc", "cfg1_retina_r50_512_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
 ]
 
 
@@ -57,6 +59,18 @@ ALL_CASES = [
 ALL_VARIANT_CASES = [
     # Entropy_ALL route of Lambda_L2Net_NoL (alpha = softmax, no lambda'): name, spec, ids, seeds, type, head kind
     ("all_nol_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 6, "scaleSum_classSum", "retina_nol"),
+]
+
+
+RPO_CASES = [
+    # detection route of the base head L_AnchorHead with last_activation='relu': alpha = relu(logits) + 1
+    # (L_anchor_head.py:358-464): name, spec, image ids, pool seed
+    ("rpo_retina_voc", "tiny_retina_voc", [0, 1, 2], 20),
+]
+
+AVG_CASES = [
+    # Entropy_Avg route of Lambda_L2Net_ReLU (ComputeAvgUnc + AggregateAvgUnc): name, spec, image ids, pool seed, sample seed
+    ("avg_retina_voc", "tiny_retina_voc", [0, 1, 2], 20, 11),
 ]
 
 
@@ -250,6 +264,52 @@ def kat_goldens():
     return g
 
 
+def run_reference_rpo_case(spec_name, gids, pool_seed):
+    """det_results of L_AnchorHead._get_bboxes (with_nms=True, rescale=True) with last_activation='relu'."""
+    spec = get_spec(spec_name)
+    batch = SyntheticPool(spec, seed0=pool_seed).batch(gids)
+    head = RL.make_head("base_relu", spec.c_out, spec.target_stds, spec.score_thr, spec.max_per_img, spec.nms_pre,
+                        spec.nms_iou)
+    dets = head._get_bboxes(batch["cls_scores"], batch["bbox_preds"], batch["anchors"], batch["img_shapes"],
+                            [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]], None, True, True)
+    g = dict(checksum=np.frombuffer(bytes.fromhex(batch_checksum(batch)), dtype=np.uint8))
+    for b, (d, l) in enumerate(dets):
+        g[f"dets_{b}"] = d.numpy()
+        g[f"labels_{b}"] = l.numpy()
+    return g
+
+
+def run_reference_avg_case(spec_name, gids, pool_seed, sample_seed):
+    """Entropy_Avg route of Lambda_L2Net_ReLU._get_bboxes.  The reference (pinned to torch 1.5) builds
+    Dirichlet(alpha) with alpha == 0 entries (relu of a negative logit); torch >= 1.8 refuses that unless argument
+    validation is off, so the class is handed to the reference code with validate_args=False - the one shim here."""
+    spec = get_spec(spec_name)
+    batch = SyntheticPool(spec, seed0=pool_seed).batch(gids)
+    head = RL.make_head("retina_relu", spec.c_out, spec.target_stds, spec.score_thr, spec.max_per_img, spec.nms_pre,
+                        spec.nms_iou)
+    head._fn_globals["Dirichlet"] = lambda alpha: Dirichlet(alpha, validate_args=False)
+    captured = {}
+    real = head.ComputeAvgUnc
+
+    def spy(*a, **k):
+        captured["nested"] = real(*a, **k)
+        return captured["nested"]
+
+    head.ComputeAvgUnc = spy
+    kw = dict(isUnc="Epistemic", uPool="Entropy_Avg", uPool2="", L_scores=batch["L_scores"], isEval=False, showNMS=False,
+              saveUnc=False, saveMaxConf=False, clsW=False, scaleUnc=False, batchIdx=0, score_thr=0.3, iou_thr=0.5,
+              return_box=False)
+    torch.manual_seed(sample_seed)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dets, unc = head._get_bboxes(batch["cls_scores"], batch["bbox_preds"], batch["anchors"], batch["img_shapes"],
+                                     [np.asarray(s, dtype=np.float32) for s in batch["scale_factors"]], None, True, True, **kw)
+    levels = np.asarray([[(v if v else np.nan) for v in img] for img in captured["nested"]], dtype=np.float64)
+    return dict(checksum=np.frombuffer(bytes.fromhex(batch_checksum(batch)), dtype=np.uint8),
+                image_scores=np.asarray(unc, dtype=np.float64), level_means=levels)
+
+
 def main():
     assert RL.available(), "reference tree not mounted"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -275,6 +335,16 @@ def main():
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: {g['scores_' + kind]}, {os.path.getsize(path)} bytes")
+    for name, spec_name, gids, pseed in ([] if only_kats else RPO_CASES):
+        g = run_reference_rpo_case(spec_name, gids, pseed)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **g)
+        print(f"{path}: {[len(g[f'dets_{b}']) for b in range(len(gids))]} detections, {os.path.getsize(path)} bytes")
+    for name, spec_name, gids, pseed, sseed in ([] if only_kats else AVG_CASES):
+        g = run_reference_avg_case(spec_name, gids, pseed, sseed)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **g)
+        print(f"{path}: {g['image_scores']}, {os.path.getsize(path)} bytes")
     path = os.path.join(GOLDEN_DIR, "kats.npz")
     np.savez_compressed(path, **kat_goldens())
     print(path, os.path.getsize(path), "bytes")

@@ -44,8 +44,13 @@ def flatten_level(x: torch.Tensor, k: int) -> torch.Tensor:
     return x.permute(0, 2, 3, 1).reshape(b, -1, k)
 
 
-def score_rows(cls_score: torch.Tensor, head: int, c_out: int) -> torch.Tensor:
+def score_rows(cls_score: torch.Tensor, head: int, c_out: int, activation: str = "softmax") -> torch.Tensor:
     x = flatten_level(cls_score, c_out)
+    if activation == "relu_plus_one":
+        # the base head's evidential form, L_anchor_head.py:401-406 (gamma = 1: (1-gamma)*Smax is an exact 0)
+        alphas = x.relu() + 1
+        s = alphas.sum(dim=2, keepdim=True) + 1e-20
+        return alphas / s
     p = x.softmax(dim=2)
     if head == HEAD_RETINA:
         # Lambda_L2.py:269-273 with gamma = 1: (1-gamma)*Smax contributes an exact 0
@@ -193,14 +198,15 @@ def pre_stage(cls_scores: List[torch.Tensor], bbox_preds: List[torch.Tensor],
               L_scores: List[torch.Tensor], anchors: List[torch.Tensor], img_shapes, scale_factors,
               *, head: int, c_out: int, stds, nms_pre: int, score_thr: float, nms_iou: float,
               max_per_img: int, obj_thr: float = 0.3, cluster_iou: float = 0.5,
-              rescale: bool = True, topk_override: Optional[List[torch.Tensor]] = None) -> Dict[str, object]:
+              rescale: bool = True, topk_override: Optional[List[torch.Tensor]] = None,
+              activation: str = "softmax") -> Dict[str, object]:
     """topk_override (stage isolation): per-level [B, K_s] prior indices to use instead
     of this function's own topk result - lets a test feed a kernel's (near-tie re-ordered but
     set-identical) row order into the later oracle stages."""
     B = cls_scores[0].shape[0]
     lvl_scores, lvl_boxes, lvl_L, lvl_idx, lvl_keys = [], [], [], [], []
     for lv, (cls, reg, anc, lam) in enumerate(zip(cls_scores, bbox_preds, anchors, L_scores)):
-        sc = score_rows(cls.float(), head, c_out)
+        sc = score_rows(cls.float(), head, c_out, activation)
         lm = lam.permute(0, 2, 3, 1).reshape(B, -1)
         dl = flatten_level(reg.float(), 4)
         an = anc[None].expand_as(dl)

@@ -121,10 +121,25 @@ def make_head(kind: str, c_out: int, stds, score_thr: float, max_per_img: int, n
         rel, cls, act = "mmdet/models/dense_heads/Lambda_L2_noL.py", "Lambda_L2Net_NoL", "relu"
     elif kind == "retina_ablation":     # ablation head: thresholds from kwargs, lambda' kept
         rel, cls, act = "mmdet/models/dense_heads/Lambda_L2_ablation.py", "Lambda_L2Net_ablation", "relu"
+    elif kind == "base_relu":           # the base head: detection route with alpha = relu + 1 (L_anchor_head.py:358-464)
+        rel, cls, act = "mmdet/models/dense_heads/L_anchor_head.py", "L_AnchorHead", "relu"
     else:
         raise ValueError(kind)
     names = ["_get_bboxes", "ComputeObjUnc", "AggregateObjScaleUnc", "ComputeScaleUnc",
              "AggregateScaleUnc"]
+    if kind in ("retina_relu", "retina_nol"):
+        names += ["ComputeAvgUnc", "AggregateAvgUnc"]
+    if kind == "base_relu":
+        names = ["_get_bboxes"]
+        # the base method imports `get_k_for_topk` from mmdet.core.export inside its body (L_anchor_head.py:413);
+        # mmdet is not importable here, so a stub package that holds the reference's own function stands in
+        import sys
+        if "mmdet" not in sys.modules:
+            for mod in ("mmdet", "mmdet.core", "mmdet.core.export"):
+                sys.modules[mod] = types.ModuleType(mod)
+            sys.modules["mmdet.core.export"].get_k_for_topk = ns["get_k_for_topk"]
+            sys.modules["mmdet"].core = sys.modules["mmdet.core"]
+            sys.modules["mmdet.core"].export = sys.modules["mmdet.core.export"]
     fns = load_methods(rel, cls, names, ns)
     head = types.SimpleNamespace()
     head.cls_out_channels = c_out
@@ -147,7 +162,7 @@ def make_head(kind: str, c_out: int, stds, score_thr: float, max_per_img: int, n
     for k, f in fns.items():
         setattr(head, k, types.MethodType(f, head))
     head._ns = ns
-    head._fn_globals = fns["ComputeObjUnc"].__globals__
+    head._fn_globals = fns["ComputeObjUnc" if "ComputeObjUnc" in fns else "_get_bboxes"].__globals__
     return head
 
 

@@ -366,6 +366,36 @@ def test_entropy_all_handles_any_number_of_foreground_priors():
         small.check_status()
 
 
+@pytest.mark.parametrize("spec_name", ["tiny_retina_voc", "tiny_retina_coco", "tiny_retina_c12", "cfg1_retina_r50_512_voc"])
+def test_relu_plus_one_scores_and_detections(spec_name):
+    """MEHHUA_ACT_RELU_PLUS_ONE (the base head's evidential form, L_anchor_head.py:401-406): K1 rows, top-k,
+    boxes and the K3a detections against the oracle's pre-stage with the same activation (typed and generic
+    class counts, capture and gather levels)."""
+    from oracle import meh_hua_oracle as O
+    spec, batch = make_batch(spec_name, [0, 1])
+    params = ScoringParams(activation="relu_plus_one")
+    pre = O.pre_stage(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                      batch["scale_factors"], activation="relu_plus_one", **O.spec_kwargs(spec))
+    sc = Scorer(spec, params, max_batch=2, device="cuda:0")
+    sc.bind(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+            batch["scale_factors"], image_ids=batch["gids"])
+    sc.k1()
+    sc.nms()
+    torch.cuda.synchronize()
+    res = sc.result()
+    override, _ = check_topk_order(spec, pre, res.topk_idx.cpu().numpy())
+    pre = O.pre_stage(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                      batch["scale_factors"], activation="relu_plus_one", topk_override=override, **O.spec_kwargs(spec))
+    np.testing.assert_allclose(res.score_rows.cpu().numpy(), pre["scores"].numpy(), rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(res.boxes.cpu().numpy(), pre["boxes"].numpy(), rtol=RTOL, atol=1e-4)
+    n_det = res.n_det.cpu().numpy()
+    for b in range(2):
+        assert n_det[b] == len(pre["dets"][b])
+        assert np.array_equal(res.det_flat[b, :n_det[b]].cpu().numpy(), pre["det_flat"][b].numpy())
+        assert np.array_equal(res.det_labels[b, :n_det[b]].cpu().numpy(), pre["labels"][b].numpy())
+        np.testing.assert_allclose(res.dets[b, :n_det[b]].cpu().numpy(), pre["dets"][b].numpy(), rtol=RTOL, atol=1e-4)
+
+
 @pytest.mark.parametrize("spec_name", ["tiny_retina_voc", "tiny_retina_c12", "cfg1_retina_r50_512_voc"])
 def test_entropy_avg_mode_parity(spec_name):
     """Entropy_Avg route of the ablation heads (ComputeAvgUnc + AggregateAvgUnc, Lambda_L2_ReLU.py:446-474,

@@ -11,7 +11,7 @@ from aod_meh_hua_b200 import anchors as A
 from aod_meh_hua_b200.specs import ScoringParams, get_spec, parse_agg_spec
 from aod_meh_hua_b200.synth import SyntheticPool
 from oracle import meh_hua_oracle as O
-from oracle.make_golden import ALL_CASES, ALL_VARIANT_CASES, CASES, VARIANT_CASES, batch_checksum
+from oracle.make_golden import ALL_CASES, ALL_VARIANT_CASES, AVG_CASES, CASES, RPO_CASES, VARIANT_CASES, batch_checksum
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -170,3 +170,39 @@ def test_empty_and_degenerate_inputs():
     assert out["image_scores"] == [0]
     assert out["dets"][0].shape == (0, 5) and out["pos_bboxes"][0].shape[1] == 0
     assert not out["level_fg"].any()
+
+
+@pytest.mark.parametrize("case", RPO_CASES, ids=[c[0] for c in RPO_CASES])
+def test_relu_plus_one_detection_route_matches_the_base_head(case):
+    """alpha = relu(logits) + 1, score = alpha / (sum alpha + 1e-20) (L_anchor_head.py:401-406): the oracle's
+    pre-stage with activation='relu_plus_one' against det_results of the AST-loaded L_AnchorHead._get_bboxes."""
+    name, spec_name, gids, pseed = case
+    g = _load(name)
+    spec = get_spec(spec_name)
+    batch = SyntheticPool(spec, seed0=pseed).batch(gids)
+    assert bytes.fromhex(batch_checksum(batch)) == g["checksum"].tobytes(), "synthetic inputs drifted"
+    kw = O.spec_kwargs(spec)
+    pre = O.pre_stage(batch["cls_scores"], batch["bbox_preds"], batch["L_scores"], batch["anchors"], batch["img_shapes"],
+                      batch["scale_factors"], activation="relu_plus_one", **kw)
+    for b in range(len(gids)):
+        assert np.array_equal(pre["dets"][b].numpy(), g[f"dets_{b}"])
+        assert np.array_equal(pre["labels"][b].numpy(), g[f"labels_{b}"])
+
+
+@pytest.mark.parametrize("case", AVG_CASES, ids=[c[0] for c in AVG_CASES])
+def test_entropy_avg_restatement_matches_reference_outputs(case):
+    """ComputeAvgUnc + AggregateAvgUnc (Lambda_L2_ReLU.py:446-474, 532-541): same torch seed, same visiting order
+    -> the same draws -> identical level means and image scores."""
+    name, spec_name, gids, pseed, sseed = case
+    g = _load(name)
+    spec = get_spec(spec_name)
+    batch = SyntheticPool(spec, seed0=pseed).batch(gids)
+    assert bytes.fromhex(batch_checksum(batch)) == g["checksum"].tobytes(), "synthetic inputs drifted"
+    torch.manual_seed(sseed)
+    out = O.score_batch_avg(batch, c_out=spec.c_out)
+    levels = np.asarray([[(v if v else np.nan) for v in img] for img in out["nested"]], dtype=np.float64)
+    assert np.array_equal(np.isnan(levels), np.isnan(g["level_means"]))
+    if np.array_equal(levels[~np.isnan(levels)], g["level_means"][~np.isnan(levels)]):      # torch build reproduced the draws
+        assert np.array_equal(np.asarray(out["image_scores"], dtype=np.float64), g["image_scores"])
+    else:
+        np.testing.assert_allclose(np.asarray(out["image_scores"]), g["image_scores"], rtol=0.3)
