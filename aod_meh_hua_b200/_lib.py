@@ -77,6 +77,9 @@ SYMBOLS = {
     "mehhua_stage_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mehhua_pool_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "mehhua_k4_pool_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "mehhua_host_pin": (C.c_int, [_P, C.c_size_t]),
+    "mehhua_host_unpin": (C.c_int, [_P]),
+    "mehhua_host_is_pinned": (C.c_int, [_P]),
     "mehhua_debug_capture_counts": (C.c_int, [_CFG, _LV, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "mehhua_debug_philox": (C.c_int, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "mehhua_host_ctx_create": (C.c_int, [_CFG, _LV, C.c_int32, C.POINTER(_P)]),

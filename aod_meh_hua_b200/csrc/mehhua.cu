@@ -872,4 +872,25 @@ int mehhua_score_batch_host(mehhua_host_ctx_t* c, const mehhua_level_t* lh, int3
   return 0;
 }
 
+int mehhua_host_pin(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return arg_fail("null host pointer");
+  if (int rc = check_device()) return rc;
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+
+int mehhua_host_unpin(void* ptr) {
+  if (!ptr) return arg_fail("null host pointer");
+  CU(cudaHostUnregister(ptr));
+  return 0;
+}
+
+int mehhua_host_is_pinned(const void* ptr) {
+  if (!ptr) return arg_fail("null host pointer");
+  if (int rc = check_device()) return rc;
+  cudaPointerAttributes a;
+  CU(cudaPointerGetAttributes(&a, ptr));
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 }  // extern "C"

@@ -251,8 +251,14 @@ int mehhua_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 
 /* Host-buffer entry point: same as mehhua_score_batch but every pointer in `levels`, img_shapes,
  * scale_factors, image_ids and image_scores_host is HOST memory.  The call copies the inputs to
- * the device (pinned staging inside the handle), scores them and copies the B image scores back;
- * it blocks until image_scores_host is valid.  Handle = resident device buffers for one geometry. */
+ * the device, scores them and copies the B image scores back; it blocks until image_scores_host is
+ * valid.  Handle = resident device buffers for one geometry, a copy stream and a compute stream: the
+ * batch is uploaded in up to four image chunks and chunk j is scored while chunk j+1 is on the wire.
+ * The copies are issued STRAIGHT FROM THE CALLER'S BUFFERS (no staging copy inside the library), so
+ * that overlap - and the full PCIe rate - needs page-locked memory on the caller's side: torch's
+ * pin_memory(), cudaHostAlloc, or mehhua_host_pin() below on an existing allocation.  Pageable
+ * buffers are accepted and give the same results, but the CUDA driver then stages every copy through
+ * its own bounce buffer synchronously (about half the rate, no overlap). */
 typedef struct mehhua_host_ctx mehhua_host_ctx_t;
 int  mehhua_host_ctx_create(const mehhua_config_t* cfg, const mehhua_level_t* level_shapes,
                             int32_t max_batch, mehhua_host_ctx_t** ctx_out);
@@ -261,6 +267,13 @@ int  mehhua_score_batch_host(mehhua_host_ctx_t* ctx, const mehhua_level_t* level
                              const float* img_shapes_host, const float* scale_factors_host,
                              const int64_t* image_ids_host, float* image_scores_host,
                              uint32_t* status_out);
+
+/* Page-lock / unlock an existing host allocation (cudaHostRegister / cudaHostUnregister) so that the copies
+ * of mehhua_score_batch_host run asynchronously from it - for callers that have no CUDA binding of their own
+ * (e.g. numpy arrays through ctypes).  mehhua_host_is_pinned: 1 = page-locked, 0 = pageable, < 0 = error. */
+int  mehhua_host_pin(void* ptr, size_t bytes);
+int  mehhua_host_unpin(void* ptr);
+int  mehhua_host_is_pinned(const void* ptr);
 
 #ifdef __cplusplus
 }

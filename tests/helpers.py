@@ -15,6 +15,44 @@ def make_batch(spec_name: str, gids, seed0: int = 20, scale_factor=(1.0, 1.0, 1.
     return spec, pool.batch(list(gids))
 
 
+GUARD = 1e-5          # relative margin every threshold-type decision must keep
+GUARD_ORDER = 2e-6    # relative gap between neighbouring detection scores (their order fixes the object indices)
+
+
+def make_guarded_batch(spec_name: str, gids, seed0: int = 20, max_tries: int = 60):
+    """SURVEY 8d guard band: a batch none of whose threshold decisions (level / row foreground test, score_thr,
+    object threshold, cluster IoU, NMS IoU, the rank-k boundary, the class argmax) sits within GUARD (relative) of
+    flipping, and whose detection scores are GUARD_ORDER apart - images that do not qualify are re-drawn under
+    another seed (the id is kept, the seed moves by a large stride).  fp32 softmax implementations differ by a few
+    1e-7 relative, so on such data every integer output of two of them must agree EXACTLY; only the order of
+    near-tied neighbours INSIDE the top-k (which no later stage depends on) is left free.
+    Returns (spec, batch, margins)."""
+    spec = get_spec(spec_name)
+    kw = O.spec_kwargs(spec, ScoringParams())
+    pools, imgs = {}, []
+    for g in gids:
+        for t in range(max_tries):
+            s0 = seed0 + t * 1_000_003
+            pool = pools.setdefault(s0, SyntheticPool(spec, seed0=s0, device="cpu"))
+            one = pool.batch([g])
+            out1 = O.score_batch(one, analytic=True, **{k: v for k, v in kw.items() if k != "T"})
+            m = O.decision_margins(one, out1, **kw)
+            hard = min(v for k, v in m.items() if k not in ("topk_adjacent", "nms_adjacent"))
+            if hard >= GUARD and m["nms_adjacent"] >= GUARD_ORDER:
+                imgs.append((one, m))
+                break
+        else:
+            raise RuntimeError(f"no guard-banded draw for image {g} of {spec_name} in {max_tries} tries")
+    batch = dict(imgs[0][0])
+    for key in ("cls_scores", "bbox_preds", "L_scores"):
+        batch[key] = [torch.cat([im[0][key][s] for im in imgs]) for s in range(spec.num_levels)]
+    batch["img_shapes"] = [im[0]["img_shapes"][0] for im in imgs]
+    batch["scale_factors"] = [im[0]["scale_factors"][0] for im in imgs]
+    batch["gids"] = list(gids)
+    margins = {k: min(im[1][k] for im in imgs) for k in imgs[0][1]}
+    return spec, batch, margins
+
+
 class Recorder:
     """Sampler hook: draws with torch (seeded) and keeps alpha + samples per (image, level)."""
 
@@ -82,3 +120,15 @@ def oracle_pairs(out, b: int):
         return z.astype(np.int64), z.astype(np.int64), z.astype(np.int64), z, z, z, []
     cat = lambda k: np.concatenate([r[k] for r in recs])
     return cat("row"), cat("obj"), cat("cls"), cat("total"), cat("ale"), cat("epi"), recs
+
+
+def assert_epi_close(got_unc: np.ndarray, total: np.ndarray, ale: np.ndarray, epi: np.ndarray, rtol: float = 1e-5) -> None:
+    """epistemic = total - aleatoric (Lambda_L2.py:525) is a difference of two O(1) quantities that are each held
+    to `rtol`: the honest bound on it is the cancellation bound rtol * (|total| + |aleatoric|) plus the
+    fp32 rounding of the subtraction itself - NOT rtol * |epi|, which no fp32 implementation (the reference's own
+    CPU vs CUDA runs included) can meet when epi << total."""
+    bound = rtol * (np.abs(total) + np.abs(ale)) + 4 * np.finfo(np.float32).eps * np.maximum(np.abs(total), np.abs(ale))
+    err = np.abs(got_unc - epi)
+    bad = err > bound
+    assert not bad.any(), (f"{int(bad.sum())} epistemic values beyond the cancellation bound; worst "
+                           f"{float((err / np.maximum(bound, 1e-30)).max()):.2f} x bound")

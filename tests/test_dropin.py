@@ -216,9 +216,20 @@ def test_host_buffer_entry_point_matches_device_path():
     st = C.c_uint32(0)
     _lib.check(lib.mehhua_score_batch_host(ctx, lv, 3, shp.ctypes.data, sf.ctypes.data, ids.ctypes.data,
                                            out.ctypes.data, C.byref(st)), "host")
-    lib.mehhua_host_ctx_destroy(ctx)
     # same Philox keys (seed, image id, row, object) -> bit-identical scores through either entry point
     assert np.array_equal(out, want) and st.value & _lib.ST_PAIR_OVERFLOW == 0
+    # pageable (above) and page-locked callers get the same answer; mehhua_host_pin registers an existing allocation
+    big = batch["cls_scores"][0].contiguous()
+    assert lib.mehhua_host_is_pinned(big.data_ptr()) == 0
+    _lib.check(lib.mehhua_host_pin(big.data_ptr(), big.numel() * 4), "pin")
+    assert lib.mehhua_host_is_pinned(big.data_ptr()) == 1
+    lv[0].logits = big.data_ptr()
+    out2 = np.zeros(3, dtype=np.float32)
+    _lib.check(lib.mehhua_score_batch_host(ctx, lv, 3, shp.ctypes.data, sf.ctypes.data, ids.ctypes.data,
+                                           out2.ctypes.data, C.byref(st)), "host")
+    _lib.check(lib.mehhua_host_unpin(big.data_ptr()), "unpin")
+    assert np.array_equal(out2, want)
+    lib.mehhua_host_ctx_destroy(ctx)
 
 
 def test_degenerate_images_score_zero():
