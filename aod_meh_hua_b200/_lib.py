@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmehhua.so")
 MAX_LEVELS = 8
 MAX_DETS = 256
 MAX_NMS_PRE = 4096
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 E_ARG, E_WORKSPACE, E_CUDA, E_NODEVICE = -1, -2, -3, -4
 ST_PAIR_OVERFLOW, ST_SELECT_SLOWPATH, ST_BAD_ALPHA, ST_CAPTURE_FALLBACK = 1, 2, 4, 8
@@ -77,6 +77,8 @@ SYMBOLS = {
     "mehhua_stage_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mehhua_pool_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "mehhua_k4_pool_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "mehhua_mi_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
+    "mehhua_mi_score_batch": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "mehhua_host_pin": (C.c_int, [_P, C.c_size_t]),
     "mehhua_host_unpin": (C.c_int, [_P]),
     "mehhua_host_is_pinned": (C.c_int, [_P]),

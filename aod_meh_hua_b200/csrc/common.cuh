@@ -14,10 +14,21 @@ constexpr int kMaxLevels = MEHHUA_MAX_LEVELS;
 // whose estimate misses (fewer than k or more than kCapRows parked rows) falls back to the select
 // over all keys and the strided gather - results are identical either way.
 constexpr int kCapRows = 4096;
-constexpr int kCapPad = 4;            // floats after the C exponentials of a parked row: 1/sum, score normaliser, 2 unused
-constexpr int kCapStride = 32;
-constexpr int kCapTargetNum = 7, kCapTargetDen = 4;
-constexpr int kCapMinRatio = 16;
+// floats of a parked row: the C exponentials, 1/sum, the score normaliser, padded to a multiple of 4 (16-byte rows:
+// vector stores in K1a, one bulk-async copy per row in K1c)
+__host__ __device__ constexpr int cap_row_floats(int C) { return (C + 2 + 3) & ~3; }
+#ifndef MEHHUA_CAP_STRIDE
+#define MEHHUA_CAP_STRIDE 32
+#endif
+#ifndef MEHHUA_CAP_TARGET_NUM
+#define MEHHUA_CAP_TARGET_NUM 7
+#endif
+#ifndef MEHHUA_CAP_MIN_RATIO
+#define MEHHUA_CAP_MIN_RATIO 8
+#endif
+constexpr int kCapStride = MEHHUA_CAP_STRIDE;
+constexpr int kCapTargetNum = MEHHUA_CAP_TARGET_NUM, kCapTargetDen = 4;
+constexpr int kCapMinRatio = MEHHUA_CAP_MIN_RATIO;
 constexpr int kCapSampleMax = 8192;   // sampled priors per (image, level) the threshold kernel can hold
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -79,7 +90,7 @@ struct Workspace {
   float* tau;                  // [B, S]   capture threshold of a capture level (K1t)
   int* cap_cnt;                // [B, S]   rows captured so far / in total
   unsigned long long* cap_comp;// [B, n_cap_levels, kCapRows] composite (key bits << 32 | ~position) of each captured row
-  float* cap_scores;           // [B, n_cap_levels, kCapRows, C + kCapPad] exponentials + normalisers of each captured row
+  float* cap_scores;           // [B, n_cap_levels, kCapRows, cap_row_floats(C)] exponentials + normalisers of each captured row
   int* row_slot;               // [B, K]   capture slot of a kept row, -1 = take it from the logits (gather)
   size_t bytes;
 };

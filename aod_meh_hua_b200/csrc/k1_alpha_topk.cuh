@@ -205,7 +205,7 @@ k1a_keys_kernel(const __grid_constant__ Plan p, float* __restrict__ keys, int* _
       if (park && slot < kCapRows) {
         const size_t e = ((size_t)b * p.n_cap_levels + L.cap) * kCapRows + slot;
         cap_comp[e] = k1_composite(key, a * L.HW + hw);
-        float* dst = cap_scores + e * (C + kCapPad);
+        float* dst = cap_scores + e * cap_row_floats(C);
         if constexpr (C % 4 == 0) {
 #pragma unroll
           for (int c = 0; c < C; c += 4) __stcs(reinterpret_cast<float4*>(dst + c), make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]));
@@ -356,6 +356,48 @@ __device__ __forceinline__ void k1_load_logits(const LevelDev& L, const int b, c
   }
 }
 
+// delta2bbox of prior n = (hw, a) of level L (core/bbox/coder/delta_xywh_bbox_coder.py:205-267): denormalise, clamp
+// dw/dh, exp, centre/size -> corners, clip to the image, divide by the scale factor; explicitly rounded fp32 ops.
+__device__ __forceinline__ float4 k1_decode_box(const Plan& p, const LevelDev& L, const int b, const int n, const int a,
+                                                const int hw, const float* __restrict__ img_shapes,
+                                                const float* __restrict__ scale_factors) {
+  float4 box;
+  const float* __restrict__ dp = L.deltas + ((size_t)(b * L.A + a) * 4) * L.HW + hw;
+  const float4 an = __ldg(reinterpret_cast<const float4*>(L.anchors) + n);
+  const float dx = __fadd_rn(__fmul_rn(__ldg(dp), p.stds[0]), p.means[0]);
+  const float dy = __fadd_rn(__fmul_rn(__ldg(dp + (size_t)L.HW), p.stds[1]), p.means[1]);
+  float dw = __fadd_rn(__fmul_rn(__ldg(dp + 2 * (size_t)L.HW), p.stds[2]), p.means[2]);
+  float dh = __fadd_rn(__fmul_rn(__ldg(dp + 3 * (size_t)L.HW), p.stds[3]), p.means[3]);
+  const float px = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f);
+  const float py = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
+  const float pw = __fsub_rn(an.z, an.x);
+  const float ph = __fsub_rn(an.w, an.y);
+  const float dxw = __fmul_rn(pw, dx);
+  const float dyh = __fmul_rn(ph, dy);
+  dw = fminf(fmaxf(dw, -p.max_ratio), p.max_ratio);
+  dh = fminf(fmaxf(dh, -p.max_ratio), p.max_ratio);
+  const float gw = __fmul_rn(pw, expf(dw));
+  const float gh = __fmul_rn(ph, expf(dh));
+  const float gx = __fadd_rn(px, dxw);
+  const float gy = __fadd_rn(py, dyh);
+  const float hgw = __fmul_rn(gw, 0.5f), hgh = __fmul_rn(gh, 0.5f);
+  box.x = __fsub_rn(gx, hgw);
+  box.y = __fsub_rn(gy, hgh);
+  box.z = __fadd_rn(gx, hgw);
+  box.w = __fadd_rn(gy, hgh);
+  const float imh = __ldg(img_shapes + 2 * b), imw = __ldg(img_shapes + 2 * b + 1);
+  box.x = box.x < 0.f ? 0.f : box.x;  box.y = box.y < 0.f ? 0.f : box.y;
+  box.z = box.z < 0.f ? 0.f : box.z;  box.w = box.w < 0.f ? 0.f : box.w;
+  box.x = box.x > imw ? imw : box.x;  box.y = box.y > imh ? imh : box.y;
+  box.z = box.z > imw ? imw : box.z;  box.w = box.w > imh ? imh : box.w;
+  if (p.rescale) {
+    const float4 sf = __ldg(reinterpret_cast<const float4*>(scale_factors) + b);
+    box.x = __fdiv_rn(box.x, sf.x);  box.y = __fdiv_rn(box.y, sf.y);
+    box.z = __fdiv_rn(box.z, sf.z);  box.w = __fdiv_rn(box.w, sf.w);
+  }
+  return box;
+}
+
 // What K1c produces for one kept row r = prior n of level L (used by the gather and rescan kernels):
 // softmax row (bit-identical to K1a's arithmetic), score row, lambda, decoded box, row max /
 // argmax, and the number of NMS candidates of the row.
@@ -405,40 +447,7 @@ __device__ __forceinline__ void k1_row_body(const Plan& p, const LevelDev& L, co
     row_argmax[(size_t)b * p.K + r] = arg;
     lam_rows[(size_t)b * p.K + r] = __ldg(L.lam + (size_t)(b * L.A + a) * L.HW + hw);
 
-    // delta2bbox: denormalise, clamp dw/dh, exp, centre/size -> corners, clip, rescale
-    const float* __restrict__ dp = L.deltas + ((size_t)(b * L.A + a) * 4) * L.HW + hw;
-    const float4 an = __ldg(reinterpret_cast<const float4*>(L.anchors) + n);
-    const float dx = __fadd_rn(__fmul_rn(__ldg(dp), p.stds[0]), p.means[0]);
-    const float dy = __fadd_rn(__fmul_rn(__ldg(dp + (size_t)L.HW), p.stds[1]), p.means[1]);
-    float dw = __fadd_rn(__fmul_rn(__ldg(dp + 2 * (size_t)L.HW), p.stds[2]), p.means[2]);
-    float dh = __fadd_rn(__fmul_rn(__ldg(dp + 3 * (size_t)L.HW), p.stds[3]), p.means[3]);
-    const float px = __fmul_rn(__fadd_rn(an.x, an.z), 0.5f);
-    const float py = __fmul_rn(__fadd_rn(an.y, an.w), 0.5f);
-    const float pw = __fsub_rn(an.z, an.x);
-    const float ph = __fsub_rn(an.w, an.y);
-    const float dxw = __fmul_rn(pw, dx);
-    const float dyh = __fmul_rn(ph, dy);
-    dw = fminf(fmaxf(dw, -p.max_ratio), p.max_ratio);
-    dh = fminf(fmaxf(dh, -p.max_ratio), p.max_ratio);
-    const float gw = __fmul_rn(pw, expf(dw));
-    const float gh = __fmul_rn(ph, expf(dh));
-    const float gx = __fadd_rn(px, dxw);
-    const float gy = __fadd_rn(py, dyh);
-    const float hgw = __fmul_rn(gw, 0.5f), hgh = __fmul_rn(gh, 0.5f);
-    box.x = __fsub_rn(gx, hgw);
-    box.y = __fsub_rn(gy, hgh);
-    box.z = __fadd_rn(gx, hgw);
-    box.w = __fadd_rn(gy, hgh);
-    const float imh = __ldg(img_shapes + 2 * b), imw = __ldg(img_shapes + 2 * b + 1);
-    box.x = box.x < 0.f ? 0.f : box.x;  box.y = box.y < 0.f ? 0.f : box.y;
-    box.z = box.z < 0.f ? 0.f : box.z;  box.w = box.w < 0.f ? 0.f : box.w;
-    box.x = box.x > imw ? imw : box.x;  box.y = box.y > imh ? imh : box.y;
-    box.z = box.z > imw ? imw : box.z;  box.w = box.w > imh ? imh : box.w;
-    if (p.rescale) {
-      const float4 sf = __ldg(reinterpret_cast<const float4*>(scale_factors) + b);
-      box.x = __fdiv_rn(box.x, sf.x);  box.y = __fdiv_rn(box.y, sf.y);
-      box.z = __fdiv_rn(box.z, sf.z);  box.w = __fdiv_rn(box.w, sf.w);
-    }
+    box = k1_decode_box(p, L, b, n, a, hw, img_shapes, scale_factors);
     reinterpret_cast<float4*>(boxes)[(size_t)b * p.K + r] = box;
     bmax = fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w));
 }
@@ -504,14 +513,14 @@ __device__ __forceinline__ void k1_flush_rows(const float* tile /* warp's [32][s
 // grid = (ceil(K / 128), B); rows of dense / direct levels are left to the rescan kernel.
 // ------------------------------------------------------------------------------------------
 template <int C, int HEAD>
-__global__ void __launch_bounds__(kGatherThreads)
+__global__ void __launch_bounds__(kGatherThreads, 3)
 k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
                   const float* __restrict__ scale_factors, const int* __restrict__ topk_idx,
                   float* __restrict__ score_rows, float* __restrict__ lam_rows,
                   float* __restrict__ boxes, float* __restrict__ row_max, int* __restrict__ row_argmax,
                   unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
                   unsigned* __restrict__ cand_maxc, const int* __restrict__ row_slot,
-                  const float* __restrict__ cap_scores) {
+                  const float* __restrict__ cap_scores, const int skip_parked) {
   const int b = blockIdx.y;
   const int r = blockIdx.x * kGatherThreads + threadIdx.x;
   int ncand = 0;
@@ -521,15 +530,16 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
   float* tile_row = (C > 0) ? tile + threadIdx.x * K1Tile<C>::stride : nullptr;
   if (r < p.K) {
     const LevelDev& L = p.lv[level_of_row(p, r)];
-    if (L.rescan == 0) {
+    const int slot0 = (C > 0 && L.rescan == 0 && L.cap >= 0) ? row_slot[(size_t)b * p.K + r] : -1;
+    if (L.rescan == 0 && !(skip_parked && slot0 >= 0)) {      // parked rows: k1c_parked_kernel's, when it runs
       const int n = topk_idx[(size_t)b * p.K + r];
       const int hw = n / L.A;
       float x[C > 0 ? C : 1];
       bool parked = false;
       if constexpr (C > 0) {
-        const int slot = (L.cap >= 0) ? row_slot[(size_t)b * p.K + r] : -1;
+        const int slot = slot0;
         if (slot >= 0) {        // capture level: the row was parked by K1a (one contiguous read): exponentials + normalisers
-          const float* src = cap_scores + (((size_t)b * p.n_cap_levels + L.cap) * kCapRows + slot) * (C + kCapPad);
+          const float* src = cap_scores + (((size_t)b * p.n_cap_levels + L.cap) * kCapRows + slot) * cap_row_floats(C);
           float inv, den;
           if constexpr (C % 4 == 0) {
 #pragma unroll
@@ -557,6 +567,190 @@ k1c_gather_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
   }
   if constexpr (C > 0) k1_flush_rows<C>(tile + (threadIdx.x & ~31) * K1Tile<C>::stride, srow);
   k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1c (parked form): the kept rows of the capture levels.  K1a left every such row as one contiguous,
+// 16-byte aligned record in the workspace (C exponentials, 1/sum, score normaliser), so nothing is
+// recomputed from the logits.  One warp owns 32 consecutive rows of an image:
+//   stage : lane i issues ONE bulk-async copy (cp.async.bulk, the TMA engine's linear form) of its row's
+//           record into the warp's shared-memory slab; all 32 copies are in flight at once and signal a
+//           per-warp mbarrier with their byte count - no registers are tied up while the rows travel;
+//   rows  : the warp walks its rows one at a time, lane = class (c = lane + 32 j): scores with the same
+//           two multiplications K1a's composite was built from (row_max == key bit for bit), coalesced
+//           store of the score row, max / first argmax by two warp REDUX, NMS candidates appended to a
+//           per-warp queue in shared memory (one atomic per flush, not per row);
+//   boxes : lane = row again: lambda, delta2bbox, row max / argmax, one coalesced store each.
+// Rows that were not parked (a level whose capture estimate missed) are left to k1c_gather_kernel.
+// grid = (ceil(K / (32 * kParkWarps)), B).
+// ------------------------------------------------------------------------------------------
+constexpr int kParkWarps = 4;
+constexpr int kParkQueue = 128;       // NMS candidates a warp queues between two flushes
+__host__ __device__ inline size_t k1c_parked_smem(int C, bool bulk) {
+  return (size_t)kParkWarps * ((bulk ? 32 * (size_t)cap_row_floats(C) * sizeof(float) : 0) + kParkQueue * 8 + 16);
+}
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (ok == 0u);
+}
+// one linear bulk copy global -> shared, completion counted in bytes on the mbarrier (16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// BULK = true : rows staged by bulk-async copies as described above;
+// BULK = false: no staging - the warp reads each record straight from global memory (three coalesced 128-byte
+//               loads per 80-class row), four rows in flight per warp.
+template <int HEAD, bool BULK>
+__global__ void __launch_bounds__(kParkWarps * 32)
+k1c_parked_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
+                  const float* __restrict__ scale_factors, const int* __restrict__ topk_idx,
+                  float* __restrict__ score_rows, float* __restrict__ lam_rows, float* __restrict__ boxes,
+                  float* __restrict__ row_max, int* __restrict__ row_argmax, unsigned long long* __restrict__ cand,
+                  int* __restrict__ cand_cnt, unsigned* __restrict__ cand_maxc, const int* __restrict__ row_slot,
+                  const float* __restrict__ cap_scores) {
+  extern __shared__ __align__(128) unsigned char park_smem[];
+  const unsigned full = 0xffffffffu;
+  const int C = p.C, NF = p.num_fg, RF = cap_row_floats(C);     // typed class counts only: RF <= 96
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const size_t per_warp = (BULK ? 32 * (size_t)RF * sizeof(float) : 0) + kParkQueue * 8 + 16;
+  unsigned char* wbase = park_smem + warp * per_warp;
+  const float* slab = reinterpret_cast<const float*>(wbase);                                   // [32][RF] (BULK)
+  unsigned long long* queue = reinterpret_cast<unsigned long long*>(wbase + (BULK ? 32 * (size_t)RF * sizeof(float) : 0));
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(queue + kParkQueue);
+  const unsigned a_slab = (unsigned)__cvta_generic_to_shared(wbase);
+
+  const int r0 = (blockIdx.x * kParkWarps + warp) * 32;
+  const int r = r0 + lane;
+  int slot = -1, lv = 0;
+  if (r < p.K) {
+    lv = level_of_row(p, r);
+    if (p.lv[lv].rescan == 0 && p.lv[lv].cap >= 0) slot = row_slot[(size_t)b * p.K + r];
+  }
+  const unsigned pm = __ballot_sync(full, slot >= 0);
+  if (pm == 0u) return;                                                                          // warp-uniform
+  const float* src = nullptr;
+  if (slot >= 0) src = cap_scores + (((size_t)b * p.n_cap_levels + p.lv[lv].cap) * kCapRows + slot) * RF;
+  if constexpr (BULK) {
+    // ---- stage: 32 bulk copies in flight, one mbarrier phase
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, (unsigned)(__popc(pm) * RF * (int)sizeof(float)));
+    }
+    __syncwarp(full);
+    if (slot >= 0) bulk_g2s(a_slab + (unsigned)(lane * RF * (int)sizeof(float)), src, (unsigned)(RF * sizeof(float)), bar);
+  }
+  // what the box phase needs (while the rows travel)
+  float lam = 0.f;
+  float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (slot >= 0) {
+    const LevelDev& L = p.lv[lv];
+    const int n = topk_idx[(size_t)b * p.K + r];
+    const int hw = n / L.A, a = n - hw * L.A;
+    lam = __ldg(L.lam + (size_t)(b * L.A + a) * L.HW + hw);
+    box = k1_decode_box(p, L, b, n, a, hw, img_shapes, scale_factors);
+  }
+  if constexpr (BULK) mbar_wait(bar, 0);
+  // ---- rows: lane = class
+  const unsigned lt = (1u << lane) - 1u;
+  int qn = 0;
+  float my_best = -1.f;
+  int my_arg = 0;
+  bool my_has = false;
+  auto flush = [&]() {
+    if (qn == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cand_cnt + b, qn);
+    base = __shfl_sync(full, base, 0);
+    __syncwarp(full);
+    unsigned long long* dst = cand + (size_t)b * p.K * NF + base;
+    for (int i = lane; i < qn; i += 32) dst[i] = queue[i];
+    __syncwarp(full);
+    qn = 0;
+  };
+  // one row whose record sits in v[] (chunk j = floats 32 j + lane), 1/sum and the score normaliser at floats C, C + 1
+  auto do_row = [&](const int i, const float (&v)[3]) {
+    const int jn = C >> 5, ln = C & 31;                   // chunk / lane that hold float C (ln <= 30: C is never 31 mod 32 here)
+    const float vn = jn == 0 ? v[0] : (jn == 1 ? v[1] : v[2]);
+    const float inv = __shfl_sync(full, vn, ln), den = __shfl_sync(full, vn, ln + 1);
+    float* dst = score_rows + ((size_t)b * p.K + r0 + i) * C;
+    float best = -1.f;
+    int arg = 0;
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = 32 * j + lane;
+      if (32 * j >= C) break;
+      float sc = 0.f;
+      if (c < C) {
+        sc = k1_score<HEAD>(v[j], inv, den);
+        dst[c] = sc;
+        if (sc > best) { best = sc; arg = c; }
+      }
+      const bool is_cand = c < NF && sc > p.score_thr;
+      const unsigned cm = __ballot_sync(full, is_cand);
+      if (cm != 0u) {
+        if (qn + 32 > kParkQueue) flush();
+        if (is_cand)
+          queue[qn + __popc(cm & lt)] = ((unsigned long long)__float_as_uint(sc) << 32) |
+                                       (unsigned long long)(0xffffffffu - (unsigned)((r0 + i) * NF + c));
+        qn += __popc(cm);
+        any = true;
+      }
+    }
+    // row maximum and its first class: order-preserving bits, two REDUX
+    const unsigned ob = f2ord(best);
+    const unsigned om = __reduce_max_sync(full, ob);
+    const int am = (int)__reduce_min_sync(full, ob == om ? (unsigned)arg : 0x7fffffffu);
+    if (lane == i) { my_best = ord2f(om); my_arg = am; my_has = any; }
+  };
+  const unsigned long long my_src = reinterpret_cast<unsigned long long>(src);
+  for (unsigned m = pm; m != 0u;) {
+    int idx[4];
+    float v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                          // up to four rows in flight
+      idx[u] = -1;
+      if (m != 0u) { idx[u] = __ffs(m) - 1; m &= m - 1u; }
+      const int i = idx[u] < 0 ? 0 : idx[u];
+      const float* row = BULK ? slab + i * RF : reinterpret_cast<const float*>(__shfl_sync(full, my_src, i));
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int c = 32 * j + lane;
+        v[u][j] = (idx[u] >= 0 && c < RF) ? (BULK ? row[c] : __ldcs(row + c)) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (idx[u] >= 0) do_row(idx[u], v[u]);
+  }
+  flush();
+  // ---- boxes: lane = row
+  if (slot >= 0) {
+    const size_t o = (size_t)b * p.K + r;
+    row_max[o] = my_best;
+    row_argmax[o] = my_arg;
+    lam_rows[o] = lam;
+    reinterpret_cast<float4*>(boxes)[o] = box;
+  }
+  float wmax = my_has ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -FLT_MAX;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(full, wmax, o));
+  if (lane == 0 && wmax > -FLT_MAX) atomicMax(cand_maxc + b, f2ord(wmax));
 }
 
 // ------------------------------------------------------------------------------------------

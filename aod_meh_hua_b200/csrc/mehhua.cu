@@ -17,6 +17,7 @@
 #include "k3_hua.cuh"
 #include "k4_pool_topk.cuh"
 #include "ka_entropy_all.cuh"
+#include "km_mutual_info.cuh"
 
 using namespace mehhua;
 
@@ -73,6 +74,16 @@ bool no_capture() {
   return v;
 }
 
+bool no_parked_kernel() {      // MEHHUA_NO_PARKED_KERNEL=1: parked rows are read by the thread-per-row gather kernel (A/B, tests)
+  static const bool v = [] { const char* e = getenv("MEHHUA_NO_PARKED_KERNEL"); return e && e[0] == '1'; }();
+  return v;
+}
+
+bool parked_bulk() {           // MEHHUA_PARKED_BULK=1: the parked rows are staged in shared memory by bulk-async copies (A/B, tests)
+  static const bool v = [] { const char* e = getenv("MEHHUA_PARKED_BULK"); return e && e[0] == '1'; }();
+  return v;
+}
+
 int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool need_ptrs, Plan* out) {
   if (!cfg || !lv) return arg_fail("null config / levels");
   if (cfg->num_levels < 1 || cfg->num_levels > kMaxLevels) return arg_fail("num_levels must be 1..8");
@@ -119,14 +130,19 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
     L.rescan = (!L.topk || (long long)MEHHUA_RESCAN_RATIO * L.k >= n) ? 1 : 0;
     L.rtile0 = (int)rtile0;
     if (L.rescan) rtile0 += (long long)L.tpp * L.A;
-    // sparse top-k levels of the class counts with a register-resident instantiation are captured
-    // while K1a streams them (k1_alpha_topk.cuh); MEHHUA_NO_CAPTURE=1 in the environment forces the gather form
     L.cap = -1;
-    if (L.topk && !L.rescan && n >= (long long)kCapMinRatio * L.k && k1_has_typed(cfg->head, cfg->c_out) &&
-        cfg->mode == MEHHUA_MODE_NMS && !no_capture())
-      L.cap = p.n_cap_levels++;
     n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
   }
+  // Capture (k1_alpha_topk.cuh): sparse top-k levels of the class counts with a register-resident instantiation have
+  // their rows parked while K1a streams them - when few of the level's priors are kept (n >= kCapMinRatio * k: few
+  // warps pay for parking) or when the level is a small part of the image (16 n <= N: whatever parking costs there is
+  // small next to a second, strided pass over it).  MEHHUA_NO_CAPTURE=1 in the environment forces the gather form.
+  if (k1_has_typed(cfg->head, cfg->c_out) && cfg->mode == MEHHUA_MODE_NMS && !no_capture())
+    for (int s = 0; s < p.S; ++s) {
+      LevelDev& L = p.lv[s];
+      if (L.topk && !L.rescan && ((long long)L.n >= (long long)kCapMinRatio * L.k || 16ll * L.n <= n_off))
+        L.cap = p.n_cap_levels++;
+    }
   if (n_off > (1ll << 30) || k_off > (1 << 20) || tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
   p.N = (int)n_off; p.K = (int)k_off; p.tiles_per_image = (int)tile0; p.rtiles_per_image = (int)rtile0;
   p.row_stride = cfg->mode == MEHHUA_MODE_ALL ? cfg->pair_cap : p.K;
@@ -171,7 +187,7 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   const size_t o_capc = take((size_t)p.B * p.S * sizeof(int));
   const size_t o_slot = take((size_t)p.B * p.K * sizeof(int));
   const size_t o_ccomp = take((size_t)p.B * p.n_cap_levels * kCapRows * sizeof(unsigned long long));
-  const size_t o_cscore = take((size_t)p.B * p.n_cap_levels * kCapRows * (p.C + kCapPad) * sizeof(float));
+  const size_t o_cscore = take((size_t)p.B * p.n_cap_levels * kCapRows * cap_row_floats(p.C) * sizeof(float));
   if (ws) {
     char* b = static_cast<char*>(base);
     ws->keys = reinterpret_cast<float*>(b + o_keys);
@@ -291,10 +307,26 @@ int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes,
   timer_mark(st, 2);
   bool any_gather = false;
   for (int s = 0; s < p.S; ++s) any_gather |= p.lv[s].rescan == 0;
+  // kept rows of the capture levels: parked records, staged by bulk-async copies (typed class counts only)
+  const bool parked = C > 0 && p.n_cap_levels > 0 && !no_parked_kernel();
+  if (parked) {
+    const dim3 grid((p.K + 32 * kParkWarps - 1) / (32 * kParkWarps), p.B);
+    if (parked_bulk()) {
+      if (int rc = ensure_dyn_smem(k1c_parked_kernel<HEAD, true>, k1c_parked_smem(p.C, true))) return rc;
+      k1c_parked_kernel<HEAD, true><<<grid, 32 * kParkWarps, k1c_parked_smem(p.C, true), st>>>(
+          p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max, o->row_argmax,
+          ws.cand, ws.cand_cnt, ws.cand_maxc, ws.row_slot, ws.cap_scores);
+    } else {
+      k1c_parked_kernel<HEAD, false><<<grid, 32 * kParkWarps, k1c_parked_smem(p.C, false), st>>>(
+          p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max, o->row_argmax,
+          ws.cand, ws.cand_cnt, ws.cand_maxc, ws.row_slot, ws.cap_scores);
+    }
+    LAUNCHED("k1c_parked_kernel");
+  }
   if (any_gather) {
     k1c_gather_kernel<C, HEAD><<<dim3((p.K + kGatherThreads - 1) / kGatherThreads, p.B), kGatherThreads, 0, st>>>(
         p, img_shapes, scale_factors, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
-        o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc, ws.row_slot, ws.cap_scores);
+        o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc, ws.row_slot, ws.cap_scores, parked ? 1 : 0);
     LAUNCHED("k1c_gather_kernel");
   }
   if (p.rtiles_per_image > 0) {
@@ -635,7 +667,11 @@ int mehhua_stage_timing_end(double* ms_sum, int32_t* calls_out) {
   return 0;
 }
 
-size_t mehhua_pool_topk_workspace_bytes(int64_t n) { (void)n; return 256; }
+// any k <= n is served: small pools by one block (256 bytes of status), large ones by the grid-wide form
+size_t mehhua_pool_topk_workspace_bytes(int64_t n) {
+  if (n < kPoolMultiMin) return 256;
+  return k4m_workspace_bytes((long long)n, (int)std::min<int64_t>(n, 0x7fffffffll));
+}
 
 int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k, int64_t* idx_out,
                         int32_t* n_selected_out, void* workspace, size_t workspace_bytes, void* stream) {
@@ -645,6 +681,43 @@ int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int
   if (workspace_bytes < 256) return MEHHUA_E_WORKSPACE;
   if (n < 0 || n > 0x7fffffffll || k < 0) return arg_fail("pool size / k");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k > n) k = (int32_t)n;
+  // large pools: grid-wide radix select + chunk sort + merges, when the workspace holds its buffers
+  if (n >= kPoolMultiMin && k > 0 && workspace_bytes >= k4m_workspace_bytes((long long)n, k)) {
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    PoolState* ps = reinterpret_cast<PoolState*>(w);
+    int* ghist = reinterpret_cast<int*>(w + 256);
+    const size_t cap = k4m_buf_elems((long long)n, k);
+    unsigned long long* buf0 = reinterpret_cast<unsigned long long*>(w + k4m_state_bytes());
+    unsigned long long* buf1 = buf0 + cap;
+    CU(cudaMemsetAsync(w, 0, k4m_state_bytes(), st));
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long per_block = (long long)kPoolHistThreads * kSelUnroll;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(2ll * sms, (n + per_block - 1) / per_block));
+    for (int pass = 0; pass < kPoolPasses; ++pass) {
+      k4m_hist_kernel<<<grid, kPoolHistThreads, 0, st>>>(scores, mask, (long long)n, k, pass, ps, ghist);
+      LAUNCHED("k4m_hist_kernel");
+    }
+    k4m_compact_kernel<<<grid, kPoolHistThreads, 0, st>>>(scores, mask, (long long)n, ps, buf0, (long long)cap);
+    LAUNCHED("k4m_compact_kernel");
+    const int chunks = (int)(cap / kPoolChunk);
+    if (int rc2 = ensure_dyn_smem(k4m_chunk_sort_kernel, (size_t)kPoolChunk * 8)) return rc2;
+    k4m_chunk_sort_kernel<<<chunks, 1024, (size_t)kPoolChunk * 8, st>>>(ps, buf0);
+    LAUNCHED("k4m_chunk_sort_kernel");
+    unsigned long long *src = buf0, *dst = buf1;
+    const int mgrid = (int)((cap / kPoolMergeVT + 255) / 256);
+    for (long long run = kPoolChunk; run < (long long)cap; run *= 2) {
+      k4m_merge_kernel<<<mgrid, 256, 0, st>>>(ps, src, dst, run);
+      LAUNCHED("k4m_merge_kernel");
+      std::swap(src, dst);
+    }
+    k4m_output_kernel<<<std::max(1, std::min(sms, (k + 255) / 256)), 256, 0, st>>>(ps, src, k, reinterpret_cast<long long*>(idx_out),
+                                                                                   n_selected_out);
+    LAUNCHED("k4m_output_kernel");
+    return 0;
+  }
   if (int rc = ensure_dyn_smem(k4_pool_topk_kernel, kPoolSmem)) return rc;
   k4_pool_topk_kernel<<<1, kPoolThreads, kPoolSmem, st>>>(scores, mask, (long long)n, k,
                                                          reinterpret_cast<long long*>(idx_out), n_selected_out,
@@ -668,6 +741,55 @@ int mehhua_debug_capture_counts(const mehhua_config_t* cfg, const mehhua_level_t
   for (int b = 0; b < B; ++b)
     for (int s = 0; s < p.S; ++s)
       if (p.lv[s].cap < 0) counts_out[b * p.S + s] = -1;
+  return 0;
+}
+
+// KM: ensemble / MC-dropout mutual-information baseline
+static int mi_plan(const float* const* member_logits, int32_t M, const mehhua_level_t* lv, int32_t S, int32_t n_cls,
+                   int32_t B, bool need_ptrs, MiPlan* out) {
+  if (!lv || S < 1 || S > kMaxLevels || M < 1 || M > kMiMaxMembers || n_cls < 1 || B < 1) return arg_fail("MI geometry");
+  MiPlan& p = *out;
+  memset(&p, 0, sizeof(p));
+  p.S = S; p.B = B; p.M = M; p.n_cls = n_cls;
+  long long tile0 = 0;
+  for (int s = 0; s < S; ++s) {
+    if (lv[s].H < 1 || lv[s].W < 1 || lv[s].A < 1) return arg_fail("level geometry");
+    p.HW[s] = lv[s].H * lv[s].W; p.A[s] = lv[s].A;
+    p.tpp[s] = (p.HW[s] + kMiThreads - 1) / kMiThreads;
+    p.tile0[s] = (int)tile0;
+    tile0 += (long long)p.tpp[s] * p.A[s];
+    for (int m = 0; m < M; ++m) {
+      if (need_ptrs && (!member_logits || !member_logits[m * S + s])) return arg_fail("null member logits");
+      p.logits[m][s] = member_logits ? member_logits[m * S + s] : nullptr;
+    }
+  }
+  if (tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
+  p.tiles_per_image = (int)tile0;
+  return 0;
+}
+
+size_t mehhua_mi_workspace_bytes(const mehhua_level_t* levels, int32_t num_levels, int32_t B) {
+  MiPlan p;
+  if (mi_plan(nullptr, 1, levels, num_levels, 1, B, false, &p)) return 0;
+  return ((size_t)B * p.tiles_per_image * sizeof(float) + 255) & ~(size_t)255;
+}
+
+int mehhua_mi_score_batch(const float* const* member_logits, int32_t n_members, const mehhua_level_t* levels,
+                          int32_t num_levels, int32_t n_cls, int32_t B, float* level_mi, float* image_scores,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!image_scores || !workspace) return arg_fail("null MI pointer");
+  MiPlan p;
+  rc = mi_plan(member_logits, n_members, levels, num_levels, n_cls, B, true, &p);
+  if (rc) return rc;
+  if (workspace_bytes < mehhua_mi_workspace_bytes(levels, num_levels, B)) return MEHHUA_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* tile_sum = static_cast<float*>(workspace);
+  km_mi_tiles_kernel<<<B * p.tiles_per_image, kMiThreads, 0, st>>>(p, tile_sum);
+  LAUNCHED("km_mi_tiles_kernel");
+  km_mi_finish_kernel<<<B, 32 * kMaxLevels, 0, st>>>(p, tile_sum, level_mi, image_scores);
+  LAUNCHED("km_mi_finish_kernel");
   return 0;
 }
 

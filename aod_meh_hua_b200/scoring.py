@@ -322,7 +322,8 @@ def pool_topk(scores: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None)
     k = int(min(max(k, 0), n))
     out = torch.empty(max(k, 1), dtype=torch.int64, device=scores.device)
     nsel = torch.zeros(1, dtype=torch.int32, device=scores.device)
-    ws = torch.zeros(256, dtype=torch.uint8, device=scores.device)
+    ws_bytes = int(lib.mehhua_pool_topk_workspace_bytes(n))      # 256 for small pools, the grid-wide form's buffers for large ones
+    ws = (torch.zeros if ws_bytes <= 256 else torch.empty)(ws_bytes, dtype=torch.uint8, device=scores.device)
     mp = None
     if mask is not None:
         mask = mask.to(device=scores.device, dtype=torch.uint8).contiguous()
@@ -330,7 +331,7 @@ def pool_topk(scores: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None)
     st = torch.cuda.current_stream(scores.device).cuda_stream
     with torch.cuda.device(scores.device):       # the library launches on the current device
         _lib.check(lib.mehhua_k4_pool_topk(scores.data_ptr(), mp, n, k, out.data_ptr(), nsel.data_ptr(),
-                                           ws.data_ptr(), 256, st), "mehhua_k4_pool_topk")
+                                           ws.data_ptr(), ws_bytes, st), "mehhua_k4_pool_topk")
     return out[: int(nsel.item())]
 
 

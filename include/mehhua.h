@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MEHHUA_ABI_VERSION 5
+#define MEHHUA_ABI_VERSION 6
 #define MEHHUA_MAX_LEVELS 8
 #define MEHHUA_MAX_DETS 256      /* upper bound on max_per_img */
 #define MEHHUA_MAX_NMS_PRE 4096  /* upper bound on nms_pre */
@@ -239,6 +239,19 @@ size_t mehhua_pool_topk_workspace_bytes(int64_t n);
 int    mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k,
                            int64_t* idx_out, int32_t* n_selected_out, void* workspace,
                            size_t workspace_bytes, void* stream);
+
+/* KM: mutual-information score of the ensemble / MC-dropout baselines.  Replaces ComputeMI
+ * (apis/CalEnsembleUnc.py:166-181, three members) and ComputeMCDropoutMI (apis/CalMCDropoutUnc.py:185-201,
+ * n stochastic passes): p_m = sigmoid(logits_m), avg = mean_m p_m, total = -sum_c avg ln avg,
+ * ale = mean_m(-sum_c p_m ln p_m), level value = mean over the level's priors of (total - ale),
+ * image score = mean over levels.  member_logits: HOST array of n_members * num_levels DEVICE pointers,
+ * [m * num_levels + s] -> member m's level-s output [B, A*n_cls, H, W] (channel = a*n_cls + c);
+ * n_members <= 32; only H, W, A of `levels` are read.  level_mi: device [B, num_levels] or NULL (the
+ * reference's `buffer`); image_scores: device [B]. */
+size_t mehhua_mi_workspace_bytes(const mehhua_level_t* levels, int32_t num_levels, int32_t B);
+int    mehhua_mi_score_batch(const float* const* member_logits, int32_t n_members, const mehhua_level_t* levels,
+                             int32_t num_levels, int32_t n_cls, int32_t B, float* level_mi, float* image_scores,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostic: rows parked per (image, level) by the last K1 call on this workspace (capture mode of K1, see
  * csrc/k1_alpha_topk.cuh), -1 for levels that are not in capture mode.  counts_out: host int32[B * num_levels]. */

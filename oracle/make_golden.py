@@ -17,6 +17,7 @@ import sys
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch.distributions import Dirichlet
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -310,6 +311,25 @@ def run_reference_avg_case(spec_name, gids, pool_seed, sample_seed):
                 image_scores=np.asarray(unc, dtype=np.float64), level_means=levels)
 
 
+def mi_goldens():
+    """ComputeMI (apis/CalEnsembleUnc.py:166-181) and ComputeMCDropoutMI (apis/CalMCDropoutUnc.py:185-201), the
+    reference's own functions, on seeded member logits."""
+    ns = dict(torch=torch, F=F, np=np)
+    import warnings
+    RL.load_functions("mmdet/apis/CalEnsembleUnc.py", ["ComputeMI"], ns)
+    from oracle.meh_hua_oracle import mi_inputs
+    ens = mi_inputs(301, 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g = dict(ensemble=np.asarray(ns["ComputeMI"](*ens, nCls=20), dtype=np.float64))
+        RL.load_functions("mmdet/apis/CalMCDropoutUnc.py", ["ComputeMCDropoutMI"], ns)
+        mc = mi_inputs(302, 7)
+        g["mcdropout"] = np.asarray(ns["ComputeMCDropoutMI"](*mc, nCls=20), dtype=np.float64)
+    g["ensemble_checksum"] = np.frombuffer(hashlib.sha256(b"".join(t.numpy().tobytes() for m in ens for t in m)).digest(), dtype=np.uint8)
+    g["mcdropout_checksum"] = np.frombuffer(hashlib.sha256(b"".join(t.numpy().tobytes() for m in mc for t in m)).digest(), dtype=np.uint8)
+    return g
+
+
 def main():
     assert RL.available(), "reference tree not mounted"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -345,6 +365,11 @@ def main():
         path = os.path.join(GOLDEN_DIR, f"{name}.npz")
         np.savez_compressed(path, **g)
         print(f"{path}: {g['image_scores']}, {os.path.getsize(path)} bytes")
+    if not only_kats:
+        path = os.path.join(GOLDEN_DIR, "mi_baselines.npz")
+        g = mi_goldens()
+        np.savez_compressed(path, **g)
+        print(f"{path}: ensemble {g['ensemble']}, mcdropout {g['mcdropout']}")
     path = os.path.join(GOLDEN_DIR, "kats.npz")
     np.savez_compressed(path, **kat_goldens())
     print(path, os.path.getsize(path), "bytes")

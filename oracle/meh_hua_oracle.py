@@ -653,3 +653,34 @@ def decision_margins(batch, out, *, head: int, c_out: int, nms_pre: int, score_t
                 io = io[np.triu_indices(len(cand), 1)]
                 m["nms_iou"] = min(m["nms_iou"], rel(io[io > 0], np.float32(nms_iou)))
     return {k: float(v) for k, v in m.items()}
+
+
+def compute_mi(members, n_cls: int = 20):
+    """Restatement of ComputeMI (mmdet/apis/CalEnsembleUnc.py:166-181) / ComputeMCDropoutMI
+    (mmdet/apis/CalMCDropoutUnc.py:185-201) for any number of members.  members[m][s]: float32
+    [B, A*n_cls, H, W].  Returns (image scores float32[B], level values float32[B, S])."""
+    M, S, B = len(members), len(members[0]), members[0][0].shape[0]
+    buffer = torch.zeros(B, S)
+    for s in range(S):
+        for b in range(B):
+            preds = torch.stack([torch.sigmoid(members[m][s][b]).permute(1, 2, 0).reshape(-1, n_cls) for m in range(M)])
+            avg = preds.mean(dim=0)                                   # :174 / :195
+            total = (-avg * avg.log()).sum(dim=1)                     # :175
+            ent = (-preds * preds.log()).sum(dim=-1)                  # :176
+            buffer[b, s] = (total - ent.mean(dim=0)).mean()           # :177-179
+    return buffer.mean(dim=-1), buffer                                # :180
+
+
+MI_SHAPES = [(9, 11), (5, 6), (3, 3), (2, 2), (1, 1)]      # level feature maps of the mutual-information goldens
+
+
+def mi_inputs(seed: int, members: int, n_cls: int = 20, anchors: int = 3, batch: int = 2):
+    """Seeded member logits of the MI goldens (numpy RandomState: the same bits on every platform):
+    members x levels of float32 [batch, anchors*n_cls, H, W], member m = a shared map + its own perturbation."""
+    rs = np.random.RandomState(seed)
+    out = [[None] * len(MI_SHAPES) for _ in range(members)]
+    for s, (h, w) in enumerate(MI_SHAPES):
+        shared = rs.standard_normal((batch, anchors * n_cls, h, w)) * 2.0 - 2.5
+        for m in range(members):
+            out[m][s] = torch.from_numpy((shared + 0.7 * rs.standard_normal(shared.shape)).astype(np.float32))
+    return out

@@ -610,6 +610,27 @@ def test_pool_topk_randomised_against_numpy():
             assert np.array_equal(got, want), (n, k, x[:5])
 
 
+def test_pool_topk_million_image_pool():
+    """cfg 5's pool: 10^6 scores, k = 2.5 % - the grid-wide form of K4 (radix select with grid-wide histograms,
+    chunk sort, merge-path merges).  Exact zeros (object-less images) make the index digits decide; k is
+    also taken beyond the non-zero scores and beyond the candidates."""
+    from aod_meh_hua_b200.scoring import pool_topk
+    rs = np.random.RandomState(77)
+    n = 1_000_000
+    x = (rs.gamma(2.0, 1.5, n)).astype(np.float32)
+    x[rs.rand(n) < 0.4] = 0.0
+    mask = rs.rand(n) < 0.9
+    xs, ms = torch.from_numpy(x).cuda(), torch.from_numpy(mask).cuda()
+    cand = np.nonzero(mask)[0]
+    order = np.argsort(x[cand], kind="stable")
+    for k in (1, 4096, 25_000, 100_001, 600_000, len(cand), n):
+        got = pool_topk(xs, k, ms).cpu().numpy()
+        want = cand[order[-k:]][::-1] if k <= len(cand) else cand[order][::-1]
+        assert np.array_equal(got, want), k
+    got = pool_topk(xs, 25_000).cpu().numpy()                   # no mask
+    assert np.array_equal(got, np.argsort(x, kind="stable")[-25_000:][::-1])
+
+
 def test_scores_do_not_depend_on_the_batch_they_were_computed_in():
     """K2 splits the samples of a pair over four warps when a launch has few pairs (<= 8192) and lets
     one warp walk them otherwise; both orders of work combine the same four partial sums in the same

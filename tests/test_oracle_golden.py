@@ -206,3 +206,16 @@ def test_entropy_avg_restatement_matches_reference_outputs(case):
         assert np.array_equal(np.asarray(out["image_scores"], dtype=np.float64), g["image_scores"])
     else:
         np.testing.assert_allclose(np.asarray(out["image_scores"]), g["image_scores"], rtol=0.3)
+
+
+def test_mutual_information_restatement_matches_the_reference_baselines():
+    """ComputeMI (apis/CalEnsembleUnc.py:166-181) and ComputeMCDropoutMI (apis/CalMCDropoutUnc.py:185-201): the
+    oracle's restatement on the seeded member logits against the outputs of the reference's own functions."""
+    g = _load("mi_baselines")
+    for key, seed, members in (("ensemble", 301, 3), ("mcdropout", 302, 7)):
+        x = O.mi_inputs(seed, members)
+        digest = hashlib.sha256(b"".join(t.numpy().tobytes() for m in x for t in m)).digest()
+        assert bytes(g[f"{key}_checksum"]) == digest
+        scores, levels = O.compute_mi(x, 20)
+        assert levels.shape == (2, len(O.MI_SHAPES))
+        np.testing.assert_array_equal(scores.double().numpy(), g[key])
