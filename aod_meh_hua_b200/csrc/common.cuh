@@ -29,6 +29,7 @@ __host__ __device__ constexpr int cap_row_floats(int C) { return (C + 2 + 3) & ~
 constexpr int kCapStride = MEHHUA_CAP_STRIDE;
 constexpr int kCapTargetNum = MEHHUA_CAP_TARGET_NUM, kCapTargetDen = 4;
 constexpr int kCapMinRatio = MEHHUA_CAP_MIN_RATIO;
+constexpr int kCapMinWarps = 16;      // sampled warps per (image, level) the stride is reduced to reach on small levels
 constexpr int kCapSampleMax = 8192;   // sampled priors per (image, level) the threshold kernel can hold
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -159,12 +160,45 @@ __device__ __forceinline__ int block_incl_scan(int v, int* warp_sums) {
 }
 
 // Bitonic sort, descending, of buf[0..n2) (n2 a power of two) by the whole block.
+// Compare-exchanges at distance < 32 never leave a warp: element e is held by thread e mod THREADS, so its
+// partner e ^ stride sits in the same warp and the exchange is a shuffle - all stages of the sizes 2..32 and the
+// last five stages of every larger size run in registers without a barrier (n2 = 2048: 28 barriers instead of 66).
+__device__ __forceinline__ unsigned long long bitonic_xchg(unsigned long long v, const int e, const int size, const int stride) {
+  const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, stride);
+  const bool keep_max = ((e & stride) == 0) == ((e & size) == 0);
+  return (keep_max == (v > o)) ? v : o;
+}
 template <int THREADS>
 __device__ __forceinline__ void block_bitonic_desc(unsigned long long* buf, int n2) {
-  for (int size = 2; size <= n2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+  if (n2 < 64) {      // tiny inputs: every stage through shared memory
+    for (int size = 2; size <= n2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
+          const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));   // stride is a power of two
+          const int hi = lo + stride;
+          const bool desc = (lo & size) == 0;
+          const unsigned long long a = buf[lo], b = buf[hi];
+          if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  // sizes 2..32 entirely in registers (n2 and THREADS are multiples of 32: whole warps take every trip together)
+  for (int e = threadIdx.x; e < n2; e += THREADS) {
+    unsigned long long v = buf[e];
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) v = bitonic_xchg(v, e, size, stride);
+    buf[e] = v;
+  }
+  __syncthreads();
+  for (int size = 64; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride >= 32; stride >>= 1) {
       for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
-        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));   // stride is a power of two
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = (lo & size) == 0;
         const unsigned long long a = buf[lo], b = buf[hi];
@@ -172,26 +206,13 @@ __device__ __forceinline__ void block_bitonic_desc(unsigned long long* buf, int 
       }
       __syncthreads();
     }
-  }
-}
-
-// Same, carrying a 16-bit payload with every key.
-template <int THREADS>
-__device__ __forceinline__ void block_bitonic_desc_kv(unsigned long long* buf, unsigned short* val, int n2) {
-  for (int size = 2; size <= n2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < (n2 >> 1); i += THREADS) {
-        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const unsigned long long a = buf[lo], b = buf[hi];
-        if ((a < b) == desc) {
-          buf[lo] = b; buf[hi] = a;
-          const unsigned short t = val[lo]; val[lo] = val[hi]; val[hi] = t;
-        }
-      }
-      __syncthreads();
+    for (int e = threadIdx.x; e < n2; e += THREADS) {
+      unsigned long long v = buf[e];
+#pragma unroll
+      for (int stride = 16; stride > 0; stride >>= 1) v = bitonic_xchg(v, e, size, stride);
+      buf[e] = v;
     }
+    __syncthreads();
   }
 }
 

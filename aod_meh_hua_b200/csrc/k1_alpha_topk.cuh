@@ -20,7 +20,7 @@ namespace mehhua {
 constexpr int kK1aThreads = 128;   // one prior position per thread, C logits in registers
 constexpr int kSelThreads = 1024;
 constexpr int kSelCap = 4096;      // >= MEHHUA_MAX_NMS_PRE
-constexpr size_t kSelSmem = kSelCap * 8 + 4096 * 4 + 40 * 4 + kSelCap * 2;
+constexpr size_t kSelSmem = kSelCap * 8 + 4096 * 4 + 40 * 4;
 constexpr int kGatherThreads = 128;
 
 // Softmax of one prior held in registers.  On return x[c] = exp(logit_c - max) (unnormalised),
@@ -245,6 +245,7 @@ k1t_threshold_kernel(const __grid_constant__ Plan p, float* __restrict__ tau, un
   const int total = wpp * L.A;
   int stride = kCapStride;
   while ((total + stride - 1) / stride > kCapSampleMax / 32) stride <<= 1;
+  while (stride > 1 && total / stride < kCapMinWarps) stride >>= 1;      // small levels: at least kCapMinWarps sampled warps, spread over the planes
   const int phase = (b * 7 + s * 3) % stride;
   const int nsw = total > phase ? (total - phase + stride - 1) / stride : 0;   // sampled warps
   const int lane = threadIdx.x & 31;
@@ -290,7 +291,6 @@ k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(k1b_smem);   // kSelCap
   int* hist = reinterpret_cast<int*>(buf + kSelCap);                            // 4096
   int* sh = hist + 4096;                                                        // 40
-  unsigned short* slot = reinterpret_cast<unsigned short*>(sh + 40);            // kSelCap
   const int s = blockIdx.x, b = blockIdx.y;
   const LevelDev& L = p.lv[s];
   if (!L.topk) return;
@@ -303,17 +303,20 @@ k1b_select_kernel(const __grid_constant__ Plan p, const float* __restrict__ keys
       const unsigned long long* cc = cap_comp + ((size_t)b * p.n_cap_levels + L.cap) * kCapRows;
       int n2 = 1;
       while (n2 < nc) n2 <<= 1;
-      for (int i = threadIdx.x; i < n2; i += kSelThreads) {
-        buf[i] = i < nc ? cc[i] : 0ull;
-        slot[i] = (unsigned short)i;
-      }
+      for (int i = threadIdx.x; i < n2; i += kSelThreads) buf[i] = i < nc ? cc[i] : 0ull;
       __syncthreads();
-      block_bitonic_desc_kv<kSelThreads>(buf, slot, n2);
+      block_bitonic_desc<kSelThreads>(buf, n2);
       for (int i = threadIdx.x; i < L.k; i += kSelThreads) {
         const int j = (int)(0xffffffffu - (unsigned)(buf[i] & 0xffffffffull));
         const int a = j / L.HW;
         out[i] = (j - a * L.HW) * L.A + a;
-        rs[i] = (int)slot[i];
+      }
+      // where did each parked record end up?  composites are distinct: its rank is found by bisection (slot = position in cc)
+      for (int i = threadIdx.x; i < nc; i += kSelThreads) {
+        const unsigned long long mine = cc[i];
+        int lo = 0, hi = n2;         // buf[lo] >= mine > buf[hi] (descending)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (buf[mid] >= mine) lo = mid; else hi = mid; }
+        if (lo < L.k) rs[lo] = i;
       }
       return;
     }

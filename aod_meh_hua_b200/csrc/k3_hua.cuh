@@ -167,13 +167,14 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
 // ------------------------------------------------------------------------------------------
 // K3b.  One block per image, rows processed in chunks of 1024 (row order = level order):
 //   (a) ordered compaction of the chunk's foreground rows (row max > fg_thr, level flagged FG);
-//   (b) one warp per foreground row, lane = object: IoU > cluster_iou -> ballot -> bit mask;
+//   (b) one thread per foreground row walks the objects: IoU > cluster_iou -> bit mask;
 //   (c) block scan of the per-row pair counts;  (d) pairs emitted in row-major (row, object)
 //   order - the order of FG_pos_bbox.nonzero().
 // Afterwards warp s averages lambda over level s's pairs (duplicates counted) in a fixed order.
 // ------------------------------------------------------------------------------------------
 constexpr int kPairThreads = 512;
-constexpr int kPairChunk = 4 * kPairThreads;
+constexpr int kPairRpt = 2;                       // rows per thread and chunk: 61 KB of shared memory, three blocks per SM
+constexpr int kPairChunk = kPairRpt * kPairThreads;
 constexpr int kPairWords = MEHHUA_MAX_DETS / 32;
 constexpr size_t kPairSmem = MEHHUA_MAX_DETS * 16 + kPairChunk * 16 + kPairChunk * kPairWords * 4 + kPairChunk * 8;
 
@@ -212,10 +213,10 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
   if (nobj > 0) {
     for (int base = 0; base < p.K; base += kPairChunk) {
       // (a) ordered compaction of foreground rows
-      const int r0 = base + 4 * threadIdx.x;
+      const int r0 = base + kPairRpt * threadIdx.x;
       int flags = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kPairRpt; ++j) {
         const int r = r0 + j;
         if (r < p.K && rmax[r] > p.fg_thr && lvl_fg[level_of_row(p, r)]) flags |= 1 << j;
       }
@@ -225,37 +226,38 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
       {
         int pos = incl - nf;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < kPairRpt; ++j)
           if (flags & (1 << j)) { fg_idx[pos] = r0 + j; fg_box[pos] = bx[r0 + j]; ++pos; }
       }
       __syncthreads();
       const int nfg = wsum[32];
-      // (b) IoU masks: warp per foreground row, lane = object
-      for (int e = w; e < nfg; e += kPairThreads / 32) {
+      // (b) IoU masks: thread = foreground row, objects walked 32 at a time (their boxes are shared-memory broadcasts)
+      for (int e = threadIdx.x; e < nfg; e += kPairThreads) {
         const float4 rb = fg_box[e];
         const float area = __fmul_rn(__fsub_rn(rb.z, rb.x), __fsub_rn(rb.w, rb.y));
         int cnt = 0;
         for (int gq = 0; gq < nwords; ++gq) {
-          const int o = gq * 32 + lane;
-          const bool hit = (o < nobj) && iou_overlaps(rb, area, obox[min(o, nobj - 1)]) > p.cluster_iou;
-          const unsigned bits = __ballot_sync(0xffffffffu, hit);
-          if (lane == 0) mask[e * kPairWords + gq] = bits;
+          unsigned bits = 0u;
+          const int on = min(32, nobj - gq * 32);
+          for (int j = 0; j < on; ++j)
+            if (iou_overlaps(rb, area, obox[gq * 32 + j]) > p.cluster_iou) bits |= 1u << j;
+          mask[e * kPairWords + gq] = bits;
           cnt += __popc(bits);
         }
-        if (lane == 0) fg_cnt[e] = cnt;
+        fg_cnt[e] = cnt;
       }
       __syncthreads();
-      // (c) scan of pair counts, four consecutive entries per thread
-      const int e0 = 4 * threadIdx.x;
+      // (c) scan of pair counts, kPairRpt consecutive entries per thread
+      const int e0 = kPairRpt * threadIdx.x;
       int c4 = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < kPairRpt; ++j)
         if (e0 + j < nfg) c4 += fg_cnt[e0 + j];
       const int incl2 = block_incl_scan<kPairThreads>(c4, wsum);
       if (threadIdx.x == kPairThreads - 1) wsum[33] = incl2;
       // (d) emit
       int pos = running + incl2 - c4;
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kPairRpt; ++j) {
         const int e = e0 + j;
         if (e >= nfg) break;
         const int cnt = fg_cnt[e];
@@ -307,15 +309,22 @@ k3b_pairs_kernel(const __grid_constant__ Plan p, const float* __restrict__ boxes
 // ------------------------------------------------------------------------------------------
 // K3c.  One block per image.  The image's ordered pair list is grouped by (object, level, class):
 // pairs are sorted by that key (bitonic sort in shared memory, pair ordinal as tie-break so every
-// group is summed in pair order - deterministic), run leaders produce the group means, and one
-// thread walks the sorted group table doing class -> level -> object aggregation with Sum / Avg /
-// Max selected per level of the hierarchy.  The shared-memory sort holds kHuaCap pairs; an image
+// group is summed in pair order - deterministic), run leaders produce the group means, then one
+// thread per OBJECT walks that object's stretch of the sorted group table (class -> level
+// aggregation with Sum / Avg / Max selected per level of the hierarchy) and thread 0 folds the
+// object values in ascending object order.  The shared-memory sort holds CAP pairs; an image
 // with more pairs is processed in several rounds over ascending object ranges (each range's pairs
-// fit; one object never has more pairs than there are rows), the walk carrying the object-level
+// fit; one object never has more pairs than there are rows), the fold carrying the object-level
 // accumulator across rounds.
+// Two instantiations are launched: CAP = kHuaCapSmall serves the images whose pairs fit it (16 KB of
+// shared memory: every image of a batch is resident at once), CAP = kHuaCap the others; a block
+// whose image belongs to the other instantiation returns at once (the pair count is only known on
+// the device).  Same arithmetic either way.
+// group key = object << 11 | level << 8 | class  (object <= 256, level < 8, class < 256)
 // ------------------------------------------------------------------------------------------
 constexpr int kHuaThreads = 256;
 constexpr int kHuaCap = 8192;
+constexpr int kHuaCapSmall = 1024;
 
 __device__ __forceinline__ float agg_combine(int op, float acc, float v) {
   return op == MEHHUA_AGG_MAX ? fmaxf(acc, v) : acc + v;
@@ -324,27 +333,30 @@ __device__ __forceinline__ float agg_finish(int op, float acc, int n) {
   return op == MEHHUA_AGG_AVG ? __fdiv_rn(acc, (float)n) : acc;
 }
 
-__host__ __device__ inline size_t k3c_smem_bytes(int S, int C) {
-  (void)S;
-  return (size_t)kHuaCap * 16 + (MEHHUA_MAX_DETS + 1) * 4 + ((C + 31) / 32) * 4 + 64 * 4;
+__host__ __device__ inline size_t k3c_smem_bytes(int cap, int C) {
+  return (size_t)cap * 16 + (MEHHUA_MAX_DETS + 1) * 4 * 3 + ((C + 31) / 32) * 4 + 64 * 4;
 }
 
+template <int CAP>
 __global__ void __launch_bounds__(kHuaThreads)
 k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
                const int* __restrict__ pair_obj, const int* __restrict__ pair_cls,
                const int* __restrict__ pair_off, const float* __restrict__ pair_unc,
                const int* __restrict__ n_obj, float* __restrict__ image_scores, unsigned* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char k3c_smem[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(k3c_smem);           // [kHuaCap]
-  unsigned* gkey = reinterpret_cast<unsigned*>(keys + kHuaCap);                          // [kHuaCap]
-  float* gval = reinterpret_cast<float*>(gkey + kHuaCap);                                // [kHuaCap]
-  int* ocnt = reinterpret_cast<int*>(gval + kHuaCap);                                    // [MAX_DETS + 1]
-  unsigned* cls_seen = reinterpret_cast<unsigned*>(ocnt + MEHHUA_MAX_DETS + 1);          // [(C+31)/32]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(k3c_smem);           // [CAP]
+  unsigned* gkey = reinterpret_cast<unsigned*>(keys + CAP);                              // [CAP]
+  float* gval = reinterpret_cast<float*>(gkey + CAP);                                    // [CAP]
+  int* ocnt = reinterpret_cast<int*>(gval + CAP);                                        // [MAX_DETS + 1] pairs per object
+  float* oval = reinterpret_cast<float*>(ocnt + MEHHUA_MAX_DETS + 1);                    // [MAX_DETS + 1] object values of a round
+  int* ohas = reinterpret_cast<int*>(oval + MEHHUA_MAX_DETS + 1);                        // [MAX_DETS + 1] object has groups
+  unsigned* cls_seen = reinterpret_cast<unsigned*>(ohas + MEHHUA_MAX_DETS + 1);          // [(C+31)/32]
   int* sh = reinterpret_cast<int*>(cls_seen + (p.C + 31) / 32);                          // 64 ints
 
   const int b = blockIdx.x;
-  const int nobj = min(n_obj[b], MEHHUA_MAX_DETS);
   const int np = pair_off[b * (p.S + 1) + p.S];
+  if ((np <= kHuaCapSmall) != (CAP == kHuaCapSmall)) return;      // the other instantiation's image
+  const int nobj = min(n_obj[b], MEHHUA_MAX_DETS);
   const int* pobj = pair_obj + (size_t)b * p.pair_cap;
   const int* pcls = pair_cls + (size_t)b * p.pair_cap;
   const float* punc = pair_unc + (size_t)b * p.pair_cap * 3;
@@ -352,21 +364,21 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
   for (int i = threadIdx.x; i < (p.C + 31) / 32; i += kHuaThreads) cls_seen[i] = 0u;
   for (int i = threadIdx.x; i <= MEHHUA_MAX_DETS; i += kHuaThreads) ocnt[i] = 0;
   __syncthreads();
-  if (np > kHuaCap) {   // pairs per object, needed to cut the object axis into ranges that fit
+  if (np > CAP) {   // pairs per object, needed to cut the object axis into ranges that fit
     for (int q = threadIdx.x; q < np; q += kHuaThreads) atomicAdd(&ocnt[min(pobj[q], MEHHUA_MAX_DETS)], 1);
     __syncthreads();
   }
-  // object-level accumulator of the walk (thread 0 only)
+  // object-level accumulator of the fold (thread 0 only)
   float oacc = 0.f;
   int on = 0;
   int o_lo = 0;
   while (o_lo < max(nobj, 1)) {
     // range [o_lo, o_hi): everything when the image fits, else as many whole objects as fit
     int o_hi = max(nobj, 1);
-    if (np > kHuaCap) {
+    if (np > CAP) {
       if (threadIdx.x == 0) {
         int acc = 0, o = o_lo;
-        while (o < nobj && acc + ocnt[o] <= kHuaCap) { acc += ocnt[o]; ++o; }
+        while (o < nobj && acc + ocnt[o] <= CAP) { acc += ocnt[o]; ++o; }
         if (o == o_lo) { atomicOr(status, MEHHUA_ST_PAIR_OVERFLOW); ++o; }   // one object alone overflows the sort
         sh[41] = o;
       }
@@ -374,20 +386,21 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
       o_hi = sh[41];
     }
     if (threadIdx.x == 0) sh[42] = 0;
+    for (int o = o_lo + threadIdx.x; o < o_hi && o <= MEHHUA_MAX_DETS; o += kHuaThreads) ohas[o] = 0;
     __syncthreads();
     // collect the range's pairs as inverted composites (descending sort -> ascending (key, ordinal))
     for (int q = threadIdx.x; q < np; q += kHuaThreads) {
       const int o = pobj[q];
       if (o >= o_lo && o < o_hi) {
         const int pos = atomicAdd(&sh[42], 1);
-        if (pos < kHuaCap) {
-          const unsigned gk = (unsigned)((o * p.S + level_of_pair(poff, p.S, q)) * p.C + pcls[q]);
+        if (pos < CAP) {
+          const unsigned gk = ((unsigned)o << 11) | ((unsigned)level_of_pair(poff, p.S, q) << 8) | (unsigned)pcls[q];
           keys[pos] = ~(((unsigned long long)gk << 32) | (unsigned)q);
         }
       }
     }
     __syncthreads();
-    const int m = min(sh[42], kHuaCap);
+    const int m = min(sh[42], CAP);
     int n2 = 1;
     while (n2 < m) n2 <<= 1;
     for (int i = m + threadIdx.x; i < n2; i += kHuaThreads) keys[i] = 0ull;
@@ -417,34 +430,40 @@ k3c_hua_kernel(const __grid_constant__ Plan p, const int* __restrict__ pair_row,
         const int gi = running + incl - 1;
         gkey[gi] = gk;
         gval[gi] = __fdiv_rn(sum, (float)cnt);
-        const unsigned cls = gk % (unsigned)p.C;
+        const unsigned cls = gk & 255u;
         atomicOr(&cls_seen[cls >> 5], 1u << (cls & 31));
       }
       __syncthreads();
       running += sh[40];
       __syncthreads();
     }
-    // one thread walks the (object, level, class)-sorted group table of the range
-    if (threadIdx.x == 0) {
-      const int ng = running;
-      int g = 0;
-      while (g < ng) {
-        const unsigned obj = gkey[g] / (unsigned)(p.S * p.C);
+    // thread o walks the stretch of the (object, level, class)-sorted group table that belongs to object o
+    const int ng = running;
+    for (int o = o_lo + threadIdx.x; o < o_hi; o += kHuaThreads) {
+      int lo = -1, hi = ng;            // first group g with object(g) >= o
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((gkey[mid] >> 11) >= (unsigned)o) hi = mid; else lo = mid; }
+      int g = hi;
+      if (g < ng && (gkey[g] >> 11) == (unsigned)o) {
         float lacc = 0.f;
         int ln = 0;
-        while (g < ng && gkey[g] / (unsigned)(p.S * p.C) == obj) {
-          const unsigned ol = gkey[g] / (unsigned)p.C;
+        while (g < ng && (gkey[g] >> 11) == (unsigned)o) {
+          const unsigned ol = gkey[g] >> 8;
           float cacc = (p.agg_class == MEHHUA_AGG_MAX) ? -FLT_MAX : 0.f;
           int cn = 0;
-          while (g < ng && gkey[g] / (unsigned)p.C == ol) { cacc = agg_combine(p.agg_class, cacc, gval[g]); ++cn; ++g; }
+          while (g < ng && (gkey[g] >> 8) == ol) { cacc = agg_combine(p.agg_class, cacc, gval[g]); ++cn; ++g; }
           const float cv = agg_finish(p.agg_class, cacc, cn);
           lacc = (ln == 0) ? cv : agg_combine(p.agg_scale, lacc, cv);
           ++ln;
         }
-        const float lv = agg_finish(p.agg_scale, lacc, ln);
-        oacc = (on == 0) ? lv : agg_combine(p.agg_object, oacc, lv);
-        ++on;
+        oval[o] = agg_finish(p.agg_scale, lacc, ln);
+        ohas[o] = 1;
       }
+    }
+    __syncthreads();
+    // fold the objects of the range in ascending order
+    if (threadIdx.x == 0) {
+      for (int o = o_lo; o < o_hi; ++o)
+        if (ohas[o]) { oacc = (on == 0) ? oval[o] : agg_combine(p.agg_object, oacc, oval[o]); ++on; }
     }
     __syncthreads();
     o_lo = o_hi;

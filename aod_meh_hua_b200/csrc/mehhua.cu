@@ -495,11 +495,16 @@ int launch_hua(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cu
   if (!o || !o->pair_row || !o->pair_obj || !o->pair_cls || !o->pair_off || !o->pair_unc || !o->n_obj ||
       !o->image_scores)
     return arg_fail("null HUA buffer");
-  const size_t smem = k3c_smem_bytes(p.S, p.C);
+  const size_t smem = k3c_smem_bytes(kHuaCap, p.C), smem_small = k3c_smem_bytes(kHuaCapSmall, p.C);
   if (smem > 227 * 1024) return arg_fail("c_out too large for the K3c shared-memory layout");
-  if (int rc = ensure_dyn_smem(k3c_hua_kernel, smem)) return rc;
-  k3c_hua_kernel<<<p.B, kHuaThreads, smem, st>>>(p, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off,
-                                                o->pair_unc, o->n_obj, o->image_scores, ws.status);
+  if (int rc = ensure_dyn_smem(k3c_hua_kernel<kHuaCap>, smem)) return rc;
+  if (int rc = ensure_dyn_smem(k3c_hua_kernel<kHuaCapSmall>, smem_small)) return rc;
+  // both instantiations: images with few pairs are served by the small one (all resident at once), the others by the large one
+  k3c_hua_kernel<kHuaCapSmall><<<p.B, kHuaThreads, smem_small, st>>>(p, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off,
+                                                                   o->pair_unc, o->n_obj, o->image_scores, ws.status);
+  LAUNCHED("k3c_hua_kernel");
+  k3c_hua_kernel<kHuaCap><<<p.B, kHuaThreads, smem, st>>>(p, o->pair_row, o->pair_obj, o->pair_cls, o->pair_off,
+                                                          o->pair_unc, o->n_obj, o->image_scores, ws.status);
   LAUNCHED("k3c_hua_kernel");
   return 0;
 }
