@@ -17,7 +17,14 @@
 
 namespace mehhua {
 
-constexpr int kK1aThreads = 128;   // one prior position per thread, C logits in registers
+#ifndef MEHHUA_K1A_THREADS
+#define MEHHUA_K1A_THREADS 32
+#endif
+// K1a / KA tile = one warp: a block retires as soon as its warp has parked its rows - with four-warp blocks nine of ten
+// blocks waited on some warp's slot atomic (measured: K1a 4.79 -> 4.64 ms per 437 cfg-3 images)
+constexpr int kK1aThreads = MEHHUA_K1A_THREADS;   // one prior position per thread, C logits in registers
+constexpr int kRescanThreads = 128;               // K1c rescan tile
+constexpr int kKaThreads = 128;                   // tile of the Entropy_ALL kernels (their plans are built with it)
 constexpr int kSelThreads = 1024;
 constexpr int kSelCap = 4096;      // >= MEHHUA_MAX_NMS_PRE
 constexpr size_t kSelSmem = kSelCap * 8 + 4096 * 4 + 40 * 4;
@@ -785,7 +792,7 @@ __device__ __forceinline__ void k1_flush_rows_at(const float* my_tile_row, float
 // to hold one.
 // ------------------------------------------------------------------------------------------
 template <int C, int HEAD>
-__global__ void __launch_bounds__(kK1aThreads, 4)
+__global__ void __launch_bounds__(kRescanThreads, 4)
 k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_shapes,
                   const float* __restrict__ scale_factors, const int* __restrict__ inv_map,
                   int* __restrict__ topk_idx, float* __restrict__ score_rows, float* __restrict__ lam_rows,
@@ -801,13 +808,14 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
     if (i < p.S && p.lv[i].rescan && ti >= p.lv[i].rtile0) s = i;
   const LevelDev& L = p.lv[s];
   const int lt = ti - L.rtile0;
-  const int a = lt / L.tpp;
-  const int hw0 = (lt - a * L.tpp) * kK1aThreads;
+  const int rtpp = (L.HW + kRescanThreads - 1) / kRescanThreads;      // rescan tiles per (image, anchor) plane
+  const int a = lt / rtpp;
+  const int hw0 = (lt - a * rtpp) * kRescanThreads;
   const int hw = hw0 + threadIdx.x;
   int ncand = 0, r = -1;
   float bmax = 0.f;
   float* srow = nullptr;
-  __shared__ float tile[(C > 0) ? (kK1aThreads * K1Tile<C>::stride) : 1];
+  __shared__ float tile[(C > 0) ? (kRescanThreads * K1Tile<C>::stride) : 1];
   if constexpr (C == 0) {
     // generic class count: rows are recomputed by streaming from global memory, one thread per prior
     float* tile_row = nullptr;
@@ -829,8 +837,8 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
     k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
   } else {
     __shared__ int s_cnt;
-    __shared__ short s_lane[kK1aThreads];      // position inside the tile of each kept prior
-    __shared__ int s_row[kK1aThreads];         // its output row
+    __shared__ short s_lane[kRescanThreads];      // position inside the tile of each kept prior
+    __shared__ int s_row[kRescanThreads];         // its output row
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     if (hw < L.HW) {

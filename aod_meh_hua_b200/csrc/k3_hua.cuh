@@ -119,12 +119,17 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
             if (i < nsb && alive[sb0 + i]) aw |= 1u << j;
           }
         int k = nk;
-        for (int i = 0; i < nsb && k < p.max_per_img; ++i) {
-          const unsigned wv = __shfl_sync(0xffffffffu, aw, i >> 5);
-          if (!((wv >> (i & 31)) & 1u)) continue;
-          if (lane < 8) aw &= ~rowmask[i * 8 + lane];
-          if (lane == 0) { kept[k] = sbox[sb0 + i]; kept_idx[k] = (unsigned short)(sb0 + i); }
-          ++k;
+        // walk the alive candidates in order, jumping over suppressed ones word by word: one step per KEPT candidate
+        for (int w = 0; w < 8 && w * 32 < nsb && k < p.max_per_img; ++w) {
+          unsigned cur = __shfl_sync(0xffffffffu, aw, w);
+          while (cur != 0u && k < p.max_per_img) {
+            const int j = __ffs(cur) - 1;
+            const int i = w * 32 + j;
+            if (lane < 8) aw &= ~rowmask[i * 8 + lane];                 // rows only hold later candidates (j' > i)
+            if (lane == 0) { kept[k] = sbox[sb0 + i]; kept_idx[k] = (unsigned short)(sb0 + i); }
+            ++k;
+            cur = __shfl_sync(0xffffffffu, aw, w) & ~((2u << j) - 1u);  // what is still alive behind i in this word
+          }
         }
         if (lane == 0) sh[44] = k;
       }

@@ -71,11 +71,11 @@ __device__ __forceinline__ bool ka_prior_fg(const Plan& p, float (&x)[C > 0 ? C 
 }
 
 template <int C, int HEAD, int ACT>
-__global__ void __launch_bounds__(kK1aThreads)
+__global__ void __launch_bounds__(kKaThreads)
 ka_fg_kernel(const __grid_constant__ Plan p, unsigned* __restrict__ fg_mask, int* __restrict__ tile_cnt,
              float* __restrict__ lam_part, unsigned* __restrict__ level_maxconf) {
-  __shared__ float wsum[kK1aThreads / 32];
-  __shared__ int wcnt[kK1aThreads / 32];
+  __shared__ float wsum[kKaThreads / 32];
+  __shared__ int wcnt[kKaThreads / 32];
   const int t = blockIdx.x;
   const int b = t / p.tiles_per_image;
   const int ti = t - b * p.tiles_per_image;
@@ -86,7 +86,7 @@ ka_fg_kernel(const __grid_constant__ Plan p, unsigned* __restrict__ fg_mask, int
   const LevelDev& L = p.lv[s];
   const int lt = ti - L.tile0;
   const int a = lt / L.tpp;
-  const int hw = (lt - a * L.tpp) * kK1aThreads + threadIdx.x;
+  const int hw = (lt - a * L.tpp) * kKaThreads + threadIdx.x;
   const bool live = hw < L.HW;
   const int CC = (C > 0) ? C : p.C;
   float lam = 0.f;
@@ -106,14 +106,14 @@ ka_fg_kernel(const __grid_constant__ Plan p, unsigned* __restrict__ fg_mask, int
   if ((threadIdx.x & 31) == 0) {
     wsum[threadIdx.x >> 5] = lam;
     wcnt[threadIdx.x >> 5] = __popc(word);
-    fg_mask[((size_t)b * p.tiles_per_image + ti) * (kK1aThreads / 32) + (threadIdx.x >> 5)] = word;
+    fg_mask[((size_t)b * p.tiles_per_image + ti) * (kKaThreads / 32) + (threadIdx.x >> 5)] = word;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     float v = 0.f;
     int n = 0;
 #pragma unroll
-    for (int w = 0; w < kK1aThreads / 32; ++w) { v += wsum[w]; n += wcnt[w]; }
+    for (int w = 0; w < kKaThreads / 32; ++w) { v += wsum[w]; n += wcnt[w]; }
     lam_part[(size_t)b * p.tiles_per_image + ti] = v;
     tile_cnt[(size_t)b * p.tiles_per_image + ti] = n;
   }
@@ -165,7 +165,7 @@ ka_scan_kernel(const __grid_constant__ Plan p, const int* __restrict__ tile_cnt,
 }
 
 template <int C, int HEAD, int ACT>
-__global__ void __launch_bounds__(kK1aThreads)
+__global__ void __launch_bounds__(kKaThreads)
 ka_rows_kernel(const __grid_constant__ Plan p, const unsigned* __restrict__ fg_mask, const int* __restrict__ tile_cnt,
                const int* __restrict__ tile_pref, const int* __restrict__ pair_off, float* __restrict__ score_rows,
                float* __restrict__ lam_rows, int* __restrict__ topk_idx, float* __restrict__ row_max,
@@ -183,8 +183,8 @@ ka_rows_kernel(const __grid_constant__ Plan p, const unsigned* __restrict__ fg_m
   const int lt = ti - L.tile0;
   const int a = lt / L.tpp;
   const int tl = lt - a * L.tpp;                       // tile of the plane
-  const int hw = tl * kK1aThreads + threadIdx.x;
-  constexpr int W = kK1aThreads / 32;
+  const int hw = tl * kKaThreads + threadIdx.x;
+  constexpr int W = kKaThreads / 32;
   const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned* masks = fg_mask + (size_t)b * p.tiles_per_image * W;
   if (!((masks[(size_t)ti * W + wi] >> lane) & 1u)) return;

@@ -123,13 +123,14 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
     L.topk = (cfg->nms_pre > 0 && cfg->nms_pre < L.n) ? 1 : 0;
     L.k = L.topk ? cfg->nms_pre : L.n;
     L.n_off = (int)n_off; L.k_off = (int)k_off;
-    L.tpp = (L.HW + kK1aThreads - 1) / kK1aThreads;
+    const int tile = cfg->mode == MEHHUA_MODE_ALL ? kKaThreads : kK1aThreads;      // the streaming kernel of the mode
+    L.tpp = (L.HW + tile - 1) / tile;
     L.tile0 = (int)tile0;
     // rows of a level come from the coalesced rescan when many priors are kept: the gather touches one
     // 32-byte sector (64-byte DRAM burst) per 4-byte logit, i.e. 8-16x the bytes it needs
     L.rescan = (!L.topk || (long long)MEHHUA_RESCAN_RATIO * L.k >= n) ? 1 : 0;
     L.rtile0 = (int)rtile0;
-    if (L.rescan) rtile0 += (long long)L.tpp * L.A;
+    if (L.rescan) rtile0 += (long long)((L.HW + kRescanThreads - 1) / kRescanThreads) * L.A;
     L.cap = -1;
     n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
   }
@@ -179,7 +180,7 @@ size_t carve(const Plan& p, void* base, Workspace* ws) {
   const size_t o_maxc = take((size_t)p.B * sizeof(unsigned));
   const size_t o_inv = take((size_t)p.B * p.N * sizeof(int));
   const bool all_mode = p.mode == MEHHUA_MODE_ALL;      // Entropy_ALL family: foreground bit masks, tile counts and prefixes
-  const size_t o_fgm = take(all_mode ? (size_t)p.B * p.tiles_per_image * (kK1aThreads / 32) * sizeof(unsigned) : 0);
+  const size_t o_fgm = take(all_mode ? (size_t)p.B * p.tiles_per_image * (kKaThreads / 32) * sizeof(unsigned) : 0);
   const size_t o_tcnt = take(all_mode ? (size_t)p.B * p.tiles_per_image * sizeof(int) : 0);
   const size_t o_tpre = take(all_mode ? (size_t)p.B * p.tiles_per_image * sizeof(int) : 0);
   const size_t o_lamp = take((size_t)p.B * p.tiles_per_image * sizeof(float));
@@ -330,7 +331,7 @@ int launch_k1_typed(const Plan& p, const Workspace& ws, const float* img_shapes,
     LAUNCHED("k1c_gather_kernel");
   }
   if (p.rtiles_per_image > 0) {
-    k1c_rescan_kernel<C, HEAD><<<p.B * p.rtiles_per_image, kK1aThreads, 0, st>>>(
+    k1c_rescan_kernel<C, HEAD><<<p.B * p.rtiles_per_image, kRescanThreads, 0, st>>>(
         p, img_shapes, scale_factors, ws.inv_map, o->topk_idx, o->score_rows, o->lam_rows, o->boxes, o->row_max,
         o->row_argmax, ws.cand, ws.cand_cnt, ws.cand_maxc);
     LAUNCHED("k1c_rescan_kernel");
@@ -371,13 +372,13 @@ int launch_k1(const Plan& p, const Workspace& ws, const float* img_shapes, const
 
 template <int C, int HEAD, int ACT>
 int launch_all_typed(const Plan& p, const Workspace& ws, const mehhua_buffers_t* o, cudaStream_t st) {
-  ka_fg_kernel<C, HEAD, ACT><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
+  ka_fg_kernel<C, HEAD, ACT><<<p.B * p.tiles_per_image, kKaThreads, 0, st>>>(
       p, ws.fg_mask, ws.tile_cnt, ws.lam_part, reinterpret_cast<unsigned*>(o->level_maxconf));
   LAUNCHED("ka_fg_kernel");
   ka_scan_kernel<<<p.B, kAllScanThreads, 0, st>>>(p, ws.tile_cnt, ws.tile_pref, ws.lam_part, o->pair_off, o->level_fg,
                                                   o->lam_mean, o->n_obj, o->n_det, ws.status);
   LAUNCHED("ka_scan_kernel");
-  ka_rows_kernel<C, HEAD, ACT><<<p.B * p.tiles_per_image, kK1aThreads, 0, st>>>(
+  ka_rows_kernel<C, HEAD, ACT><<<p.B * p.tiles_per_image, kKaThreads, 0, st>>>(
       p, ws.fg_mask, ws.tile_cnt, ws.tile_pref, o->pair_off, o->score_rows, o->lam_rows, o->topk_idx, o->row_max,
       o->row_argmax, o->pair_row, o->pair_obj, o->pair_cls);
   LAUNCHED("ka_rows_kernel");
