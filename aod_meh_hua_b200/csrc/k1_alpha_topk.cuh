@@ -785,7 +785,7 @@ __device__ __forceinline__ void k1_flush_rows_at(const float* my_tile_row, float
 // second time with K1a's coalesced tiling; a prior finds its row arithmetically (no top-k:
 // row = k_off + n) or through the inverse map K1b scattered (row or -1).  Traffic = the level's
 // logits once more, instead of ~25x the kept rows for a sector-granular gather.
-// Two phases per 128-position tile: (1) every thread loads its C logits (full coalesced lines, as in
+// Two phases per 128-position tile (positions j = a*HW + hw, flattened over the level's planes): (1) every thread loads its C logits (full coalesced lines, as in
 // K1a) and the kept ones park them in their row of the shared-memory tile and join a list;
 // (2) the listed rows are handed out to the first threads of the block, so the row arithmetic
 // (softmax, argmax, box decode, candidates) runs once per KEPT row, not once per warp that happens
@@ -808,10 +808,12 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
     if (i < p.S && p.lv[i].rescan && ti >= p.lv[i].rtile0) s = i;
   const LevelDev& L = p.lv[s];
   const int lt = ti - L.rtile0;
-  const int rtpp = (L.HW + kRescanThreads - 1) / kRescanThreads;      // rescan tiles per (image, anchor) plane
-  const int a = lt / rtpp;
-  const int hw0 = (lt - a * rtpp) * kRescanThreads;
-  const int hw = hw0 + threadIdx.x;
+  // tile = kRescanThreads consecutive positions j = a*HW + hw of the level (the order of the key array): planes
+  // smaller than a tile (SSD's last levels have 1 to 64 positions) share tiles instead of owning a mostly empty one
+  const int j = lt * kRescanThreads + threadIdx.x;
+  const bool live = j < L.n;
+  const int a = live ? j / L.HW : 0;
+  const int hw = live ? j - a * L.HW : 0;
   int ncand = 0, r = -1;
   float bmax = 0.f;
   float* srow = nullptr;
@@ -819,7 +821,7 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
   if constexpr (C == 0) {
     // generic class count: rows are recomputed by streaming from global memory, one thread per prior
     float* tile_row = nullptr;
-    if (hw < L.HW) {
+    if (live) {
       const int n = hw * L.A + a;
       float x[1];
       if (L.topk) {
@@ -839,11 +841,12 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
     __shared__ int s_cnt;
     __shared__ short s_lane[kRescanThreads];      // position inside the tile of each kept prior
     __shared__ int s_row[kRescanThreads];         // its output row
+    __shared__ int s_n[kRescanThreads];           // its prior index n = hw*A + a
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    if (hw < L.HW) {
+    if (live) {
       float x[C];
-      k1_load_logits<C>(L, b, a, hw, x);      // every thread loads: full coalesced lines, as in K1a
+      k1_load_logits<C>(L, b, a, hw, x);      // every thread loads: coalesced lines wherever a warp stays inside one plane
       if (L.topk) {
         r = inv_map[(size_t)b * p.N + L.n_off + a * L.HW + hw];
       } else {
@@ -857,6 +860,7 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
         const int pos = atomicAdd(&s_cnt, 1);
         s_lane[pos] = (short)threadIdx.x;
         s_row[pos] = r;
+        s_n[pos] = hw * L.A + a;
       }
     }
     __syncthreads();
@@ -870,7 +874,7 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
       float x[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) x[c] = tile_row[c];
-      const int n = (hw0 + src) * L.A + a;
+      const int n = s_n[threadIdx.x];
       k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
                            row_argmax, x, tile_row, ncand, bmax, srow);
     }

@@ -25,6 +25,10 @@ using namespace mehhua;
 #ifndef MEHHUA_RESCAN_RATIO
 #define MEHHUA_RESCAN_RATIO 2
 #endif
+// ... and, for levels that are not captured, when RESCAN_WIDE * k >= n
+#ifndef MEHHUA_RESCAN_WIDE
+#define MEHHUA_RESCAN_WIDE 2
+#endif
 
 namespace {
 
@@ -126,24 +130,29 @@ int build_plan(const mehhua_config_t* cfg, const mehhua_level_t* lv, int B, bool
     const int tile = cfg->mode == MEHHUA_MODE_ALL ? kKaThreads : kK1aThreads;      // the streaming kernel of the mode
     L.tpp = (L.HW + tile - 1) / tile;
     L.tile0 = (int)tile0;
-    // rows of a level come from the coalesced rescan when many priors are kept: the gather touches one
-    // 32-byte sector (64-byte DRAM burst) per 4-byte logit, i.e. 8-16x the bytes it needs
-    L.rescan = (!L.topk || (long long)MEHHUA_RESCAN_RATIO * L.k >= n) ? 1 : 0;
-    L.rtile0 = (int)rtile0;
-    if (L.rescan) rtile0 += (long long)((L.HW + kRescanThreads - 1) / kRescanThreads) * L.A;
+    L.rescan = 0;
     L.cap = -1;
     n_off += n; k_off += L.k; tile0 += (long long)L.tpp * L.A;
   }
-  // Capture (k1_alpha_topk.cuh): sparse top-k levels of the class counts with a register-resident instantiation have
-  // their rows parked while K1a streams them - when few of the level's priors are kept (n >= kCapMinRatio * k: few
-  // warps pay for parking) or when the level is a small part of the image (16 n <= N: whatever parking costs there is
-  // small next to a second, strided pass over it).  MEHHUA_NO_CAPTURE=1 in the environment forces the gather form.
-  if (k1_has_typed(cfg->head, cfg->c_out) && cfg->mode == MEHHUA_MODE_NMS && !no_capture())
-    for (int s = 0; s < p.S; ++s) {
-      LevelDev& L = p.lv[s];
-      if (L.topk && !L.rescan && ((long long)L.n >= (long long)kCapMinRatio * L.k || 16ll * L.n <= n_off))
-        L.cap = p.n_cap_levels++;
-    }
+  // Where the kept rows of a level come from (k1_alpha_topk.cuh), decided per level:
+  //   rescan  - no top-k, or at least half of the priors are kept: a second coalesced pass;
+  //   capture - sparse top-k levels of the class counts with a register-resident instantiation park their rows while
+  //             K1a streams them, when few of the level's priors are kept (n >= kCapMinRatio * k: few warps pay for
+  //             parking) or when the level is a small part of the image (16 n <= N: whatever parking costs there is
+  //             small next to a second pass over it).  MEHHUA_NO_CAPTURE=1 in the environment turns capture off;
+  //   rescan  - what is left, when at least 1 / MEHHUA_RESCAN_WIDE of the priors are kept: the strided gather touches
+  //             one 32-byte sector (64-byte DRAM burst) per 4-byte logit, i.e. as many bytes as the whole level;
+  //   gather  - the rest.
+  const bool may_capture = k1_has_typed(cfg->head, cfg->c_out) && cfg->mode == MEHHUA_MODE_NMS && !no_capture();
+  for (int s = 0; s < p.S; ++s) {
+    LevelDev& L = p.lv[s];
+    const long long n = L.n;
+    if (!L.topk || (long long)MEHHUA_RESCAN_RATIO * L.k >= n) L.rescan = 1;
+    else if (may_capture && (n >= (long long)kCapMinRatio * L.k || 16 * n <= n_off)) L.cap = p.n_cap_levels++;
+    else if ((long long)MEHHUA_RESCAN_WIDE * L.k >= n) L.rescan = 1;
+    L.rtile0 = (int)rtile0;
+    if (L.rescan) rtile0 += (n + kRescanThreads - 1) / kRescanThreads;      // tiles over the flattened (anchor, position) axis
+  }
   if (n_off > (1ll << 30) || k_off > (1 << 20) || tile0 * B > 0x7fffffffll) return arg_fail("geometry too large");
   p.N = (int)n_off; p.K = (int)k_off; p.tiles_per_image = (int)tile0; p.rtiles_per_image = (int)rtile0;
   p.row_stride = cfg->mode == MEHHUA_MODE_ALL ? cfg->pair_cap : p.K;
