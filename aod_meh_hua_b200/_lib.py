@@ -76,6 +76,7 @@ SYMBOLS = {
     "mehhua_stage_timing_begin": (C.c_int, [C.c_int32]),
     "mehhua_stage_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mehhua_pool_topk_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "mehhua_pool_topk_workspace_bytes_k": (C.c_size_t, [C.c_int64, C.c_int32]),
     "mehhua_k4_pool_topk": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "mehhua_mi_workspace_bytes": (C.c_size_t, [_P, C.c_int32, C.c_int32]),
     "mehhua_mi_score_batch": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_size_t, _P]),

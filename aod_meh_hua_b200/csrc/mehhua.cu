@@ -688,6 +688,11 @@ size_t mehhua_pool_topk_workspace_bytes(int64_t n) {
   return k4m_workspace_bytes((long long)n, (int)std::min<int64_t>(n, 0x7fffffffll));
 }
 
+size_t mehhua_pool_topk_workspace_bytes_k(int64_t n, int32_t k) {
+  if (n < kPoolMultiMin || k <= 0) return 256;
+  return k4m_workspace_bytes((long long)n, (int)std::min<int64_t>(n, (int64_t)k));
+}
+
 int mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k, int64_t* idx_out,
                         int32_t* n_selected_out, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_device();

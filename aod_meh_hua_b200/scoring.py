@@ -322,7 +322,7 @@ def pool_topk(scores: torch.Tensor, k: int, mask: Optional[torch.Tensor] = None)
     k = int(min(max(k, 0), n))
     out = torch.empty(max(k, 1), dtype=torch.int64, device=scores.device)
     nsel = torch.zeros(1, dtype=torch.int32, device=scores.device)
-    ws_bytes = int(lib.mehhua_pool_topk_workspace_bytes(n))      # 256 for small pools, the grid-wide form's buffers for large ones
+    ws_bytes = int(lib.mehhua_pool_topk_workspace_bytes_k(n, k))      # 256 for small pools, the grid-wide form's buffers for large ones
     ws = (torch.zeros if ws_bytes <= 256 else torch.empty)(ws_bytes, dtype=torch.uint8, device=scores.device)
     mp = None
     if mask is not None:

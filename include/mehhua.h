@@ -235,7 +235,10 @@ int mehhua_stage_timing_end(double* ms_sum, int32_t* calls_out);
  * in descending score order (ties: larger index first, the order a stable ascending argsort
  * followed by [-k:] would keep).  Replaces the arg[-nonZeroSize:] part of update_X_L
  * (utils/active_datasets.py:106-107, 124).  n_selected_out (device int32) = min(k, #candidates). */
-size_t mehhua_pool_topk_workspace_bytes(int64_t n);
+size_t mehhua_pool_topk_workspace_bytes(int64_t n);               /* enough for any k <= n */
+size_t mehhua_pool_topk_workspace_bytes_k(int64_t n, int32_t k);  /* enough for this k: pools >= 32 768 take the grid-wide
+                                                                    * form (state + histograms + two (k + 4096)-element buffers)
+                                                                    * when the workspace is at least this large, one block otherwise */
 int    mehhua_k4_pool_topk(const float* scores, const uint8_t* mask, int64_t n, int32_t k,
                            int64_t* idx_out, int32_t* n_selected_out, void* workspace,
                            size_t workspace_bytes, void* stream);
