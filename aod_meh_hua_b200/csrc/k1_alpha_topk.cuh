@@ -838,6 +838,23 @@ k1c_rescan_kernel(const __grid_constant__ Plan p, const float* __restrict__ img_
     }
     k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
   } else {
+    if (!L.topk) {
+      // every prior of the level is kept (block-uniform): each thread turns its own logits into its row, straight from
+      // registers - no parking in shared memory, no hand-over
+      float* tile_row = tile + threadIdx.x * K1Tile<C>::stride;
+      if (live) {
+        float x[C];
+        k1_load_logits<C>(L, b, a, hw, x);
+        const int n = hw * L.A + a;
+        r = L.k_off + n;
+        topk_idx[(size_t)b * p.K + r] = n;
+        k1_row_body<C, HEAD>(p, L, b, r, n, img_shapes, scale_factors, score_rows, lam_rows, boxes, row_max,
+                             row_argmax, x, tile_row, ncand, bmax, srow);
+      }
+      k1_flush_rows<C>(tile + (threadIdx.x & ~31) * K1Tile<C>::stride, srow);
+      k1_append_candidates(p, b, r, ncand, bmax, tile_row, cand, cand_cnt, cand_maxc);
+      return;
+    }
     __shared__ int s_cnt;
     __shared__ short s_lane[kRescanThreads];      // position inside the tile of each kept prior
     __shared__ int s_row[kRescanThreads];         // its output row

@@ -74,7 +74,7 @@ constexpr float kEm2Half = 0.067667641618306351f;     // e^-2 / 2 (tiny list: s 
 constexpr float kEm1 = 0.36787944117144233f;          // e^-1 / 1 (GS list: s = 1)
 constexpr float kTinySpan = 130.f;                    // a p<=1 draw is non-zero only when log2 x - m >= -(kTinySpan - log2 s): 126 + margin
 #ifndef MEHHUA_K2_UNROLL
-#define MEHHUA_K2_UNROLL 4
+#define MEHHUA_K2_UNROLL 2
 #endif
 constexpr int kK2Unroll = MEHHUA_K2_UNROLL;
 constexpr int kQCap = 8;                              // tiny rows a lane can remember having written in one round

@@ -16,10 +16,13 @@ namespace mehhua {
 
 constexpr int kNmsThreads = 512;
 constexpr int kNmsCap = 2048;     // candidates held in shared memory per chunk
-constexpr int kNmsChunk = 1024;   // candidates requested per chunk
+#ifndef MEHHUA_NMS_CHUNK
+#define MEHHUA_NMS_CHUNK 512
+#endif
+constexpr int kNmsChunk = MEHHUA_NMS_CHUNK;   // candidates requested per chunk
 constexpr int kNmsSub = 256;      // candidates resolved per suppression-matrix block
 // buf | sbox | kept | hist (aliased by the 256x8-word suppression matrix) | sh | class ids | alive
-constexpr size_t kNmsSmem = kNmsCap * 8 + kNmsCap * 16 + MEHHUA_MAX_DETS * 16 + 4096 * 4 + 48 * 4 + kNmsCap * 2 + kNmsCap + MEHHUA_MAX_DETS * 2;
+constexpr size_t kNmsSmem = kNmsCap * 8 + kNmsCap * 16 + MEHHUA_MAX_DETS * 16 + 4096 * 4 + 48 * 4 + kNmsCap * 2 + kNmsCap + MEHHUA_MAX_DETS * 4;
 
 // IoU of the greedy NMS: inter / (area_i + area_j - inter), areas without +1, all fp32-rounded.
 __device__ __forceinline__ float iou_nms(const float4 a, const float4 b) {
@@ -30,6 +33,25 @@ __device__ __forceinline__ float iou_nms(const float4 a, const float4 b) {
   const float inter = __fmul_rn(w, h);
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
+
+// Does candidate box `bj` of class `cj` survive the kept detections [q_lo, q_hi)?  Boxes of different classes are a class
+// offset apart, so only detections of the same class can overlap it: their classes are scanned four at a time (one
+// 64-bit shared-memory load, a zero-halfword test) and the IoU is evaluated on a match only.
+__device__ __forceinline__ bool nms_clear_of_kept(const float4* kept, const unsigned short* kept_cls, const int q_lo,
+                                                  const int q_hi, const unsigned short cj, const float4 bj, const float thr) {
+  const unsigned long long cj4 = 0x0001000100010001ull * (unsigned long long)cj;
+  for (int q = q_lo & ~3; q < q_hi; q += 4) {
+    const unsigned long long x = *reinterpret_cast<const unsigned long long*>(kept_cls + q) ^ cj4;
+    if (((x - 0x0001000100010001ull) & ~x & 0x8000800080008000ull) == 0ull) continue;     // no halfword is zero: no class match
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int qq = q + u;
+      if (qq >= q_lo && qq < q_hi && kept_cls[qq] == cj && iou_nms(kept[qq], bj) > thr) return false;
+    }
+  }
+  return true;
+}
+
 
 // ------------------------------------------------------------------------------------------
 // K3a.  Candidates are visited in descending (score, then ascending flat index) order, in sorted
@@ -55,6 +77,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
   unsigned short* scls = reinterpret_cast<unsigned short*>(sh + 48);              // kNmsCap
   unsigned char* alive = reinterpret_cast<unsigned char*>(scls + kNmsCap);        // kNmsCap
   unsigned short* kept_idx = reinterpret_cast<unsigned short*>(alive + kNmsCap);  // MAX_DETS
+  unsigned short* kept_cls = kept_idx + MEHHUA_MAX_DETS;                          // MAX_DETS: class of each kept detection
 
   const int b = blockIdx.x;
   const int NF = p.num_fg;
@@ -79,9 +102,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
       const float4 o = bx[r];
       const float off = __fmul_rn((float)c, off_unit);
       const float4 sb = make_float4(__fadd_rn(o.x, off), __fadd_rn(o.y, off), __fadd_rn(o.z, off), __fadd_rn(o.w, off));
-      unsigned char ok = 1;
-      for (int q = 0; q < nk; ++q)
-        if (iou_nms(kept[q], sb) > p.nms_iou) { ok = 0; break; }
+      const unsigned char ok = nms_clear_of_kept(kept, kept_cls, 0, nk, (unsigned short)c, sb, p.nms_iou) ? 1 : 0;
       sbox[i] = sb;
       scls[i] = (unsigned short)c;
       alive[i] = ok;
@@ -126,7 +147,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
             const int j = __ffs(cur) - 1;
             const int i = w * 32 + j;
             if (lane < 8) aw &= ~rowmask[i * 8 + lane];                 // rows only hold later candidates (j' > i)
-            if (lane == 0) { kept[k] = sbox[sb0 + i]; kept_idx[k] = (unsigned short)(sb0 + i); }
+            if (lane == 0) { kept[k] = sbox[sb0 + i]; kept_idx[k] = (unsigned short)(sb0 + i); kept_cls[k] = scls[sb0 + i]; }
             ++k;
             cur = __shfl_sync(0xffffffffu, aw, w) & ~((2u << j) - 1u);  // what is still alive behind i in this word
           }
@@ -151,9 +172,7 @@ k3a_nms_kernel(const __grid_constant__ Plan p, const unsigned long long* __restr
       if (nk < p.max_per_img && nk > nk_before) {
         for (int j = sb0 + nsb + threadIdx.x; j < cnt; j += kNmsThreads) {
           if (!alive[j]) continue;
-          const float4 bj = sbox[j];
-          for (int q = nk_before; q < nk; ++q)
-            if (iou_nms(kept[q], bj) > p.nms_iou) { alive[j] = 0; break; }
+          if (!nms_clear_of_kept(kept, kept_cls, nk_before, nk, scls[j], sbox[j], p.nms_iou)) alive[j] = 0;
         }
       }
       __syncthreads();

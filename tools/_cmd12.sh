@@ -1,0 +1,7 @@
+python -m pytest tests/test_gpu_parity.py tests/test_pool_identity.py tests/test_dropin.py tests/test_gpu_variants.py -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2_t13.log
+MEHHUA_LIB=$PWD/aod_meh_hua_b200/libmehhua_x_nc256.so python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r2_t13_nc256.log
+for w in "cfg3:" "cfg4:--workload cfg4_ssd512_coco --samples 50" "cfg5:--workload cfg5_retina_r101_1344_coco --steps 12" "cfg2:--workload cfg2_ssd300_voc"; do
+  tag=${w%%:*}; AB_ARGS="${w#*:}" tools/ab_bench.sh default x_nc512 x_nc256 > gpurun_out/ab_$tag.txt 2>&1
+  for v in default x_nc512 x_nc256; do cp gpurun_out/ab_$v.json gpurun_out/ab_${tag}_$v.json; done
+done
+cat gpurun_out/r2_t13.log gpurun_out/r2_t13_nc256.log gpurun_out/ab_cfg3.txt gpurun_out/ab_cfg4.txt gpurun_out/ab_cfg5.txt gpurun_out/ab_cfg2.txt
