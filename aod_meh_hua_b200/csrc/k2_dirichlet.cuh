@@ -184,49 +184,7 @@ __device__ __forceinline__ void k2_draw_sample(const K2Pair& W, const unsigned t
   // shared work list: one Philox block per iteration gives a Box-Muller pair of normals (one per
   // cursor) and the two acceptance uniforms; a cursor that accepts takes the next undrawn class.
   //   d = alpha - 1/3, c = 1/sqrt(9 d);  v = (1 + c x)^3;  accept iff v > 0 and ln U < x^2/2 + d - d v + d ln v;  g = d v
-  if (W.nbig == 1) {
-    // One class with alpha >= 1 (the usual case: the row's top class): both normals of a Box-Muller pair are two
-    // successive attempts for it - the second counts only when the first is rejected - so a lane needs a second
-    // Philox block with probability ~0.2 % and the warp with a few per cent (with one attempt per block the warp
-    // looped again four times out of five).
-    const float4 k = lds_v4(W.a_big4);                        // d, c, row offset, log2 d - m
-    bool pending = active;
-    unsigned kcall = 0x80000000u;
-    while (__any_sync(full, pending)) {
-      const uint4 w = k2_philox(make_uint4(t, kcall++, W.pid, W.gid), W.key);
-      const float r2 = (-2.f * kLn2) * lg2_approx(__uint_as_float(0x3f800000u | (w.x >> 9)) - 0.99999994039535522f);
-      const float r = r2 * rsqrtf(r2);
-      float sn, cs;
-      __sincosf((float)w.y * 1.4629180792671596e-09f, &sn, &cs);
-      float l2sel = 0.f;
-      bool ok = false;
-#pragma unroll
-      for (int h = 1; h >= 0; --h) {                            // h = 1: second attempt, h = 0: first (it wins when both pass)
-        const float x = h ? r * sn : r * cs;
-        const unsigned wu = h ? w.w : w.z;
-        const float v1 = fmaf(k.y, x, 1.f);
-        const float lv = lg2_approx(v1);                        // NaN for v1 < 0: never accepted
-        const float v = v1 * v1 * v1;
-        const float lnu = kLn2 * lg2_approx(__uint_as_float(0x3f800000u | (wu >> 9)) - 0.99999994039535522f);
-        float rhs = fmaf(0.5f * x, x, k.x);
-        rhs = fmaf(-k.x, v, rhs);
-        rhs = fmaf(3.f * kLn2 * k.x, lv, rhs);
-        if (lnu < rhs) { ok = true; l2sel = fmaf(3.f, lv, k.w); }
-      }
-      if (pending && ok) {
-        pending = false;
-        if (PASS == 1) {
-          mx = fmaxf(mx, l2sel);
-        } else {
-          const float d = (PASS == 0) ? l2sel : l2sel - m;
-          const float e = ex2_approx(d);
-          stage_store(W.a_lrow + __float_as_uint(k.z), e);
-          asum += e;
-          bs = fmaf(e, d, bs);
-        }
-      }
-    }
-  } else if (W.nbig > 0) {
+  if (W.nbig > 0) {
     const unsigned done_at = W.a_big4 + (unsigned)(W.nbig + 2) * 16u;
     const unsigned pad0 = W.a_big4 + (unsigned)W.nbig * 16u;
     unsigned ca = active ? W.a_big4 : pad0, cb = active ? W.a_big4 + 16u : pad0;
