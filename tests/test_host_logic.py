@@ -79,6 +79,22 @@ def test_no_cpu_fallback():
     out = (C.c_uint32 * 8)()
     rc = lib.mehhua_debug_philox((C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0), out)
     assert rc == _lib.E_NODEVICE
+    # the mutual-information baselines: CPU tensors are refused, and the entry point itself reports the missing device
+    from aod_meh_hua_b200.mi_baselines import ComputeMI, mutual_information
+    members = [[torch.zeros(1, 40, 3, 3)] for _ in range(3)]
+    with pytest.raises(_lib.MehhuaError):
+        mutual_information(members, 20)
+    with pytest.raises(_lib.MehhuaError):
+        ComputeMI(*members, nCls=20)
+    lv = _lib.LevelArray()
+    lv[0].H, lv[0].W, lv[0].A = 3, 3, 2
+    ptrs = (C.c_void_p * 3)(8, 8, 8)
+    assert lib.mehhua_mi_workspace_bytes(lv, 1, 1) >= 4
+    assert lib.mehhua_mi_score_batch(ptrs, 3, lv, 1, 20, 1, None, C.c_void_p(8), C.c_void_p(8), 256, None) == _lib.E_NODEVICE
+    # K4's workspace sizes: one block for small pools, the grid-wide form's buffers for large ones
+    assert lib.mehhua_pool_topk_workspace_bytes(1000) == 256 and lib.mehhua_pool_topk_workspace_bytes_k(1000, 10) == 256
+    big, big_k = lib.mehhua_pool_topk_workspace_bytes(1_000_000), lib.mehhua_pool_topk_workspace_bytes_k(1_000_000, 25_000)
+    assert 256 < big_k < big and big >= 2 * 8 * 1_000_000
 
 
 def test_product_package_never_imports_the_oracle():
