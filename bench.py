@@ -391,6 +391,10 @@ def main():
                     k1_stage_achieved=n_scored * spec.k1_bytes_per_image() / k1_all_s / 1e9 if k1_all_s > 0 else 0.0,
                     stage_ms_per_step=stage_avg)
     roofline["k1_stage_frac"] = roofline["k1_stage_achieved"] / peak
+    # also against the nominal 8 TB/s of HBM3e (the measured copy peak above is the denominator of `frac`)
+    roofline["nominal_peak"] = 8000.0
+    roofline["frac_of_nominal"] = achieved / 8000.0
+    roofline["k1_stage_frac_of_nominal"] = roofline["k1_stage_achieved"] / 8000.0
     # ---- the sampling stage: compute-bound (draws/s + pipe utilisation, no byte roofline)
     draws = n_scored * pairs_per_image * params.n_samples * spec.c_out
     k2 = dict(bound="issue slots / XU pipe", draws_per_s=draws / stage_tot_s["k2_dirichlet"] if stage_tot_s["k2_dirichlet"] > 0 else 0.0,
