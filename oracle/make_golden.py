@@ -39,6 +39,8 @@ CASES = [
     ("ssd_voc", "tiny_ssd_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
     # one BASELINE.json configuration at full size (config 1: RetinaNet R50-FPN 512x512, 20 VOC classes, 49 104 priors)
     ("full_cfg1_retina_voc", "cfg1_retina_r50_512_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
+    # ... and the SSD head at full size (config 2: SSD300 VGG16, 21 outputs, 8 732 priors)
+    ("full_cfg2_ssd300_voc", "cfg2_ssd300_voc", [0, 1], 20, 4321, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
 ]
 
 
