@@ -41,6 +41,8 @@ CASES = [
     ("full_cfg1_retina_voc", "cfg1_retina_r50_512_voc", [0, 1], 20, 1234, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
     # ... and the SSD head at full size (config 2: SSD300 VGG16, 21 outputs, 8 732 priors)
     ("full_cfg2_ssd300_voc", "cfg2_ssd300_voc", [0, 1], 20, 4321, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
+    # ... and the headline shape (config 3: RetinaNet R50-FPN 800x1344 COCO, 201 600 priors x 80 classes), one image
+    ("full_cfg3_retina_coco", "cfg3_retina_r50_800x1344_coco", [0], 20, 777, (1.0, 1.0, 1.0, 1.0), "objectSum_scaleMax_classSum", False),
 ]
 
 
