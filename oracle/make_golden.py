@@ -59,6 +59,8 @@ ALL_CASES = [
     # name, spec, image ids, pool seed, sample seed, aggregation type
     ("all_retina_coco", "tiny_retina_coco", [0, 1, 2], 20, 5, "scaleAvg_classAvg"),
     ("all_ssd_voc", "tiny_ssd_voc", [0, 1, 2], 20, 5, "scaleSum_classAvg"),
+    # the same route at full size (config 1: 49 104 priors, hundreds of foreground priors per image)
+    ("all_full_cfg1_retina_voc", "cfg1_retina_r50_512_voc", [0, 1], 20, 8, "scaleSum_classSum"),
 ]
 
 ALL_VARIANT_CASES = [
