@@ -8,7 +8,7 @@
 namespace mehhua {
 
 constexpr int kMaxLevels = MEHHUA_MAX_LEVELS;
-// Capture mode of K1 (sparse top-k levels, N >= kCapMinRatio * k): a pre-pass over 1/kCapStride of the level's
+// Capture mode of K1 (sparse top-k levels: n >= kCapMinRatio * k, or 16 n <= N; build_plan decides): a pre-pass over 1/kCapStride of the level's
 // warps estimates the key of rank kCapTargetNum / kCapTargetDen * k; the streaming pass parks the score row of every prior at or above
 // it (at most kCapRows per (image, level)); the select then runs over the parked rows only.  A level
 // whose estimate misses (fewer than k or more than kCapRows parked rows) falls back to the select
@@ -48,7 +48,7 @@ struct LevelDev {
   int tpp;    // K1a tiles per (image, anchor) plane
   int tile0;  // first K1a tile of the level inside one image's tile list
   int topk;   // 1 when n > k (the per-level top-k is active)
-  int rescan; // 1 when the level's rows are produced by the coalesced rescan kernel (no top-k, or k >= n/8)
+  int rescan; // 1 when the level's rows are produced by the coalesced rescan kernel (no top-k, or 2 k >= n)
   int rtile0; // first rescan tile of the level inside one image's rescan tile list
   int cap;    // >= 0: the level's rows are CAPTURED while K1a streams it (index of the level among the capture levels); -1: not
 };

@@ -1,12 +1,14 @@
 // K1: logits -> softmax / score -> ranking key (K1a, the HBM-streaming kernel) -> per-level top-k
 // (K1b, block radix select) -> the kept rows, lambda, decoded boxes, NMS candidates (K1c).
-// Where do the kept rows' scores come from?  Three forms, chosen per level by the plan:
-//   capture : sparse top-k levels (k << N).  K1t reads 1/32 of the level's warps and estimates the key of
-//             rank 2k; K1a parks the score row of every prior at or above it while the logits are in
-//             registers; K1b sorts the parked rows only; K1c reads 320-byte parked rows instead of
-//             re-reading C strided sectors per row.  A level whose estimate misses falls back to gather.
-//   gather  : the row's C logits re-read with stride H*W (one 32-byte sector per logit).
-//   rescan  : dense levels (k >= N/8 or no top-k): a second coalesced pass.
+// Where do the kept rows' scores come from?  Three forms, chosen per level by the plan (build_plan in mehhua.cu):
+//   capture : sparse top-k levels (n >= 8 k, or a level that is a small part of the image).  K1t reads 1/32 of the
+//             level's warps and estimates the key of rank 1.75 k; K1a parks the record of every prior at or above it
+//             while the logits are in registers (C exponentials + the two normalisers, one 16-byte aligned row); K1b
+//             sorts the parked composites only; K1c (k1c_parked_kernel, one warp per row) turns the records into
+//             score rows.  An (image, level) whose estimate misses falls back to the select over all keys + gather.
+//   gather  : the row's C logits re-read with stride H*W (one 32-byte sector per logit): top-k levels that are not
+//             captured, and fall-backs.
+//   rescan  : levels without a top-k, or with 2 k >= n: a second coalesced pass.
 //
 // Reference semantics: _get_bboxes per-level block (mmdet/models/dense_heads/Lambda_L2.py:264-326,
 // My_L_ssd_head.py:325-361), delta2bbox (core/bbox/coder/delta_xywh_bbox_coder.py:205-267), the
